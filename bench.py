@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's headline benchmark (BASELINE.json: "Gaussians/sec rasterized (fwd & fwd+bwd) @256^2").
+
+A "step" is one pass of the rasterizer over one batch of synthetic input: configs[1] of BASELINE.json,
+500k Gaussians x 8 views x 256x256, SH (25 coefficients, degree-3 evaluation), forward only.  Per rank the work is
+fixed (weak scaling): rank r renders views [8r, 8r+8) of the same cloud; there is no collective in the data
+path (views are independent), only an all-gather of per-view PSNR after the timed region.
+
+Reported on ONE JSON line (see the task contract):
+  value      forward Gaussians/s (= P * views / time), inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        same metric through the C ABI's host-buffer entry gs_render_host (pinned host inputs copied to the
+             device and images copied back inside the timed region)
+  fwd_bwd    forward + backward (MSE to a random target) Gaussians/s, device-resident
+  roofline   dominant kernel: algorithmic bytes per launch / its average duration (CUDA events on the launch
+             stream, recorded by the library around each stage), against MEASURED_PEAKS.json's HBM GB/s
+  cpu_baseline  the CPU oracle port (oracle/gs_oracle.c, OpenMP) timed on this box's host cores on a bounded
+             sample (whole views of the same workload)
+`--impl reference` times that CPU port alone (the reference's rasterizer is an absent external CUDA extension
+and the reference has no CPU path of its own: SURVEY.md section 0).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+P_GAUSS, VIEWS, HW, D_SH = 500_000, 8, 256, 25
+WORKLOAD = "C2: 500k Gaussians x 8 views x 256x256, SH 25 coeff (deg-3 eval), forward"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, c in zip(names, r[5:9]) if c.lower() == "active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def run_reference(args):
+    """CPU arm: the oracle port on the host cores, one whole view of the workload per step."""
+    import numpy as np
+    from oracle.gs_oracle import OracleRender
+    from pf3plat_b200.synthetic import make_scene
+    from tests.util import view_args
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    sc = make_scene(P_GAUSS, VIEWS, HW, HW, seed=0)
+    for _ in range(args.warmup):
+        st, kw = view_args(sc, 0)
+        OracleRender(st, frag_rel=0, **kw).close()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        st, kw = view_args(sc, k % VIEWS)
+        OracleRender(st, frag_rel=0, **kw).close()
+    dt = time.perf_counter() - t0
+    val = P_GAUSS * args.steps / dt
+    sample = f"{args.steps} steps x 1 view (500k Gaussians, 256x256) of the C2 workload, forward"
+    print(json.dumps({
+        "impl": "reference", "metric": "gaussians_per_sec_fwd_256", "value": val, "unit": "Gaussians/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "reference rasterizer is an absent external CUDA extension; this "
+                   "is the CPU oracle port of its algorithm, OpenMP over tiles"},
+        "cpu_baseline": {"value": val, "unit": "Gaussians/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Gaussians/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from pf3plat_b200 import _capi, rasterizer
+    from pf3plat_b200.cameras import make_view_batch
+    from pf3plat_b200.rasterizer import BatchSettings, rasterize_batch
+    from pf3plat_b200.synthetic import make_scene, make_target
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback exists)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- synthetic workload: this rank's 8 views of the shared cloud ----
+    sc = make_scene(P_GAUSS, VIEWS, HW, HW, seed=0, first_view=rank * VIEWS, total_views=world * VIEWS)
+    vb = make_view_batch(sc.extrinsics, sc.intrinsics, sc.near, sc.far, scale_invariant=True)
+    host = {
+        "means3D": sc.means.reshape(1, P_GAUSS, 3), "opacities": sc.opacities.reshape(1, P_GAUSS),
+        "shs": sc.harmonics.permute(0, 2, 1).contiguous().reshape(1, P_GAUSS, D_SH, 3),
+        "cov3D_precomp": torch.stack([sc.covariances[:, 0, 0], sc.covariances[:, 0, 1], sc.covariances[:, 0, 2],
+                                      sc.covariances[:, 1, 1], sc.covariances[:, 1, 2], sc.covariances[:, 2, 2]],
+                                     -1).reshape(1, P_GAUSS, 6),
+        "viewmatrix": vb.viewmatrix, "projmatrix": vb.projmatrix, "campos": vb.campos, "bg": sc.background,
+        "tanfov": vb.tanfov,
+    }
+    host = {k: v.contiguous().float().pin_memory() for k, v in host.items()}
+    d = {k: v.to(dev) for k, v in host.items()}
+    bs = BatchSettings(image_height=HW, image_width=HW, viewmatrix=d["viewmatrix"], projmatrix=d["projmatrix"],
+                       campos=d["campos"], bg=d["bg"], sh_degree=4, tanfov=d["tanfov"])
+
+    def fwd():
+        with torch.no_grad():
+            return rasterize_batch(bs, d["means3D"], d["opacities"], shs=d["shs"], cov3D_precomp=d["cov3D_precomp"])
+
+    target = make_target(VIEWS, HW, HW, seed=1 + rank).to(dev)
+    leaves = {k: d[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "cov3D_precomp")}
+
+    def fwd_bwd():
+        for t in leaves.values():
+            t.grad = None
+        color, _ = rasterize_batch(bs, leaves["means3D"], leaves["opacities"], shs=leaves["shs"],
+                                   cov3D_precomp=leaves["cov3D_precomp"])
+        loss = ((color - target) ** 2).mean()
+        loss.backward()
+        return loss
+
+    # ---- e2e through the C ABI with HOST buffers ----
+    L = _capi.lib()
+    out_color = torch.empty((VIEWS, 3, HW, HW), dtype=torch.float32).pin_memory()
+    out_radii = torch.empty((VIEWS, P_GAUSS), dtype=torch.int32).pin_memory()
+    hcfg = _capi.GsConfig()
+    hcfg.P, hcfg.S, hcfg.V, hcfg.M, hcfg.sh_degree = P_GAUSS, 1, VIEWS, D_SH, 4
+    hcfg.image_height = hcfg.image_width = HW
+    hcfg.scale_modifier = 1.0
+    for k in ("viewmatrix", "projmatrix", "campos", "bg", "tanfov"):
+        setattr(hcfg, k, host[k].data_ptr())
+    hin = _capi.GsInputs(means3D=host["means3D"].data_ptr(), opacities=host["opacities"].data_ptr(),
+                         shs=host["shs"].data_ptr(), cov3D_precomp=host["cov3D_precomp"].data_ptr())
+    hout = _capi.GsOutputs(color=out_color.data_ptr(), radii=out_radii.data_ptr(), depth=None)
+    h2d = sum(host[k].numel() * 4 for k in host)
+    d2h = out_color.numel() * 4 + out_radii.numel() * 4
+    stream = torch.cuda.current_stream(dev)
+    ctx = rasterizer.current_context(dev)
+
+    def e2e():
+        _capi.check(L.gs_render_host(ctx, ctypes.byref(hcfg), ctypes.byref(hin), ctypes.byref(hout), stream.cuda_stream))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    gauss_per_step = P_GAUSS * VIEWS * world
+
+    # correctness spot check + counters (outside every timed region)
+    color, radii = fwd()
+    torch.cuda.synchronize(dev)
+    stats = rasterizer.last_stats(dev)
+    launches_fwd = stats["kernel_launches"]
+    D_ours = stats["num_rendered"]
+    vis = int((radii > 0).sum().item())
+    e2e()
+    assert torch.equal(out_color.to(dev), color), "host-buffer entry and device entry disagree"
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_fwd = timed(fwd, args.steps, args.warmup)
+    clocks = sampler.stop()
+    ms_e2e = timed(e2e, args.steps, args.warmup)
+    ms_fb = timed(fwd_bwd, args.steps, args.warmup)
+    stats_fb = rasterizer.last_stats(dev)
+
+    # per-stage device time (library-recorded CUDA events on the launch stream), separate pass
+    rasterizer.set_profiling(True, dev)
+    acc = {}
+    for _ in range(max(3, args.steps // 2)):
+        fwd_bwd()
+        for k, v in rasterizer.stage_ms(dev).items():
+            acc.setdefault(k, []).append(v)
+    rasterizer.set_profiling(False, dev)
+    stage = {k: statistics.mean(v) for k, v in acc.items()}
+
+    # PSNR of each view against the target, gathered over ranks (the only collective of the job)
+    mse = ((color - target) ** 2).mean(dim=(1, 2, 3))
+    psnr = -10 * torch.log10(mse)
+    if world > 1:
+        allp = [torch.empty_like(psnr) for _ in range(world)]
+        dist.all_gather(allp, psnr)
+        psnr = torch.cat(allp)
+
+    if rank == 0:
+        hbm, hbm_src = peaks()
+        # CPU baseline on a bounded sample + the oracle's own D (upstream's 3-sigma-square definition)
+        cpu = None
+        D_ref_per_view = None
+        if not args.no_cpu_baseline:
+            from oracle.gs_oracle import OracleRender
+            from tests.util import view_args
+            cores = os.cpu_count() or 1
+            nv = 2
+            t0 = time.perf_counter()
+            Ds = []
+            for v in range(nv):
+                st, kw = view_args(sc, v)
+                r = OracleRender(st, frag_rel=0, **kw)
+                Ds.append(r.num_rendered)
+                if v == 0:
+                    err = np.abs(color[0].cpu().numpy() - r.color).max()
+                r.close()
+            dt = time.perf_counter() - t0
+            D_ref_per_view = sum(Ds) / nv
+            cpu = {"value": P_GAUSS * nv / dt, "unit": "Gaussians/s", "cores": cores, "kind": "port",
+                   "sample": f"{nv} of the 8 views (500k Gaussians, 256x256), forward, oracle/gs_oracle.c with OpenMP",
+                   "max_abs_rgb_err_view0": float(err)}
+        # algorithmic bytes; D = upstream-definition tile instances when the oracle ran
+        N = HW * HW
+        D_alg = (D_ref_per_view * VIEWS) if D_ref_per_view else D_ours
+        S_sh = 12 * D_SH
+        b_pre = 40 * P_GAUSS + S_sh * P_GAUSS + 48 * vis + 8 * P_GAUSS * VIEWS
+        b_bin = 36 * D_alg
+        b_comp = 40 * D_alg + 20 * N * VIEWS
+        b_fwd = b_pre + b_bin + b_comp
+        stages = {
+            "preprocess": {"bytes": b_pre, "ms": stage.get("preprocess")},
+            "bin": {"bytes": b_bin, "ms": stage.get("bin")},
+            "composite": {"bytes": b_comp, "ms": stage.get("composite")},
+        }
+        for s in stages.values():
+            s["achieved_gbs"] = s["bytes"] / (s["ms"] * 1e-3) / 1e9 if s["ms"] else None
+            s["frac"] = s["achieved_gbs"] / hbm if s["ms"] else None
+        dom = max(stages, key=lambda k: stages[k]["ms"] or 0)
+        line = {
+            "metric": "gaussians_per_sec_fwd_256", "value": gauss_per_step * args.steps / (ms_fwd * 1e-3),
+            "unit": "Gaussians/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_fwd / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "views_per_gpu": VIEWS, "gaussians": P_GAUSS, "image": [HW, HW],
+                       "parallelism": f"views sharded over {world} GPU(s), no data-path collective",
+                       "l2": "inputs+intermediates per step (~360 MB) exceed the 126 MB L2; no explicit flush"},
+            "views_per_sec": VIEWS * world * args.steps / (ms_fwd * 1e-3),
+            "e2e": {"value": gauss_per_step * args.steps / (ms_e2e * 1e-3), "unit": "Gaussians/s",
+                    "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "gs_render_host (C ABI, pinned host buffers)"},
+            "fwd_bwd": {"value": gauss_per_step * args.steps / (ms_fb * 1e-3), "unit": "Gaussians/s",
+                        "ms_per_step": ms_fb / args.steps, "loss": "MSE to U(0,1) target"},
+            "gpu_launches": (launches_fwd) * args.steps,
+            "gpu_launches_note": f"{launches_fwd} own kernels per forward step (+ CUB scan/sort); fwd+bwd step: "
+                                 f"{stats_fb['kernel_launches']}",
+            "roofline": {"kernel": dom, "bound": "hbm", "achieved": stages[dom]["achieved_gbs"], "peak": hbm,
+                         "unit": "GB/s", "frac": stages[dom]["frac"], "traffic": None, "peak_source": hbm_src,
+                         "note": "composite is FP32/MUFU-issue bound, not HBM bound (DESIGN.md section 6)"},
+            "roofline_stages": stages,
+            "roofline_forward": {"bytes": b_fwd, "achieved_gbs": b_fwd / (ms_fwd / args.steps * 1e-3) / 1e9,
+                                 "frac": b_fwd / (ms_fwd / args.steps * 1e-3) / 1e9 / hbm},
+            "stage_ms": stage,
+            "tile_instances": {"ours_tight": D_ours, "upstream_definition": D_alg, "visible": vis},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "psnr_vs_target_mean": float(psnr.mean().item()),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,181 @@
+/*
+ * gsplat_b200.h -- C ABI of the B200-native differentiable Gaussian-splatting rasterizer.
+ *
+ * This is the drop-in boundary for the hot path of cvlab-kaist/PF3plat: the
+ * `diff_gaussian_rasterization` extension it imports at
+ *   /root/reference/src/model/decoder/cuda_splatting.py:5-8
+ * and calls at :99-124 (perspective), :192-217 (orthographic) and, through
+ * render_depth_cuda, :255-268.  The reference has no C ABI of its own (its
+ * boundary is a pybind/torch extension, absent from the tree:
+ * /root/reference/requirements.txt:2); every entry point below names the piece
+ * of that Python surface it stands behind.  INTEGRATION.md shows the
+ * reference-side binding (the ctypes stub `diff_gaussian_rasterization/`
+ * shipped in this repo).
+ *
+ * Conventions
+ *  - plain C, no torch types; all device pointers are fp32/int32 arrays in the
+ *    CUDA device current on the calling thread; `stream` is a cudaStream_t
+ *    passed as void*.
+ *  - every function returns 0 on success or a negative GS_ERR_* code; no
+ *    exceptions cross the ABI; gs_last_error() gives a text for the calling
+ *    thread's last failure.
+ *  - 4x4 matrices are the TRANSPOSED (row-vector) matrices exactly as the
+ *    reference passes them (cuda_splatting.py:85-87), i.e. column-major flats.
+ *  - one call renders V views of S scenes (V % S == 0, view v shows scene
+ *    v / (V/S)); the reference's per-view call is S = V = 1.
+ */
+#ifndef GSPLAT_B200_H
+#define GSPLAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GS_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define GS_API __attribute__((visibility("default")))
+#else
+#define GS_API
+#endif
+
+enum {
+    GS_OK = 0,
+    GS_ERR_INVALID = -1,   /* bad argument combination (mirrors the ValueErrors of GaussianRasterizer.forward) */
+    GS_ERR_CUDA = -2,      /* a CUDA runtime call failed */
+    GS_ERR_OOM = -3,       /* device allocation failed */
+    GS_ERR_OVERFLOW = -4,  /* more than 2^31-1 tile instances */
+    GS_ERR_NO_DEVICE = -5
+};
+
+enum {
+    GS_FLAG_DEPTH = 1u,        /* also composite camera-space z as a 4th channel (render_depth_cuda mode "depth", cuda_splatting.py:226-269, fused) */
+    GS_FLAG_PREFILTERED = 2u   /* GaussianRasterizationSettings.prefiltered */
+};
+
+/* GaussianRasterizationSettings (cuda_splatting.py:99-112), batched over views. */
+typedef struct GsConfig {
+    int32_t P;            /* Gaussians per scene */
+    int32_t S;            /* scenes */
+    int32_t V;            /* views in this call */
+    int32_t M;            /* SH coefficients per channel = shs.shape[1]; 0 with colors_precomp */
+    int32_t sh_degree;    /* settings.sh_degree */
+    int32_t image_height; /* settings.image_height */
+    int32_t image_width;  /* settings.image_width */
+    uint32_t flags;       /* GS_FLAG_* */
+    float tanfovx;        /* settings.tanfovx / tanfovy: used for every view when `tanfov` is NULL */
+    float tanfovy;
+    float scale_modifier; /* settings.scale_modifier */
+    /* constants of the upstream algorithm; 0 selects the default */
+    float near_cull_z;    /* default 0.2 */
+    float dilation;       /* default 0.3 */
+    float guard_band;     /* default 1.3 */
+    int32_t sh_eval_max_degree; /* default 3 (<=0 selects it) */
+    int32_t reserved_;
+    const float *viewmatrix; /* device [V,16]  settings.viewmatrix */
+    const float *projmatrix; /* device [V,16]  settings.projmatrix */
+    const float *campos;     /* device [V,3]   settings.campos */
+    const float *bg;         /* device [V,3]   settings.bg */
+    const float *tanfov;     /* device [V,2] or NULL */
+    const float *view_scale; /* device [V] or NULL: per-view factor s applied as mean*s, cov*s^2, scales*s
+                                (the 1/near rescale of cuda_splatting.py:64-71 without materialising copies) */
+} GsConfig;
+
+/* Arguments of GaussianRasterizer.forward (cuda_splatting.py:117-124).  Exactly one of shs/colors_precomp and
+ * exactly one of (scales,rotations)/cov3D_precomp must be non-NULL, as the reference op requires. */
+typedef struct GsInputs {
+    const float *means3D;        /* device [S,P,3] */
+    const float *opacities;      /* device [S,P] */
+    const float *shs;            /* device [S,P,M,3] or NULL */
+    const float *colors_precomp; /* device [V,P,3] or NULL (per VIEW: PF3plat passes view-dependent fake colours) */
+    const float *scales;         /* device [S,P,3] or NULL */
+    const float *rotations;      /* device [S,P,4] (w,x,y,z) or NULL */
+    const float *cov3D_precomp;  /* device [S,P,6] (xx,xy,xz,yy,yz,zz) or NULL */
+} GsInputs;
+
+/* Return values of GaussianRasterizer.forward: (color, radii); depth is the opt-in extra. */
+typedef struct GsOutputs {
+    float *color;   /* device [V,3,H,W] */
+    int32_t *radii; /* device [V,P] */
+    float *depth;   /* device [V,H,W], required iff GS_FLAG_DEPTH */
+} GsOutputs;
+
+/* Incoming gradients of backward. */
+typedef struct GsOutGrads {
+    const float *dL_dcolor; /* device [V,3,H,W] */
+    const float *dL_ddepth; /* device [V,H,W] or NULL */
+} GsOutGrads;
+
+/* Gradients returned by the reference autograd Function.  Any pointer may be NULL.
+ * Per-scene gradients are SUMMED over the views of the scene inside the kernel (V/S == 1 in the drop-in). */
+typedef struct GsInGrads {
+    float *dL_dmeans3D;    /* device [S,P,3] */
+    float *dL_dmeans2D;    /* device [V,P,3] screen-space (NDC-scaled) gradient, z = 0 */
+    float *dL_dshs;        /* device [S,P,M,3] */
+    float *dL_dcolors;     /* device [V,P,3] */
+    float *dL_dopacities;  /* device [S,P] */
+    float *dL_dscales;     /* device [S,P,3] */
+    float *dL_drotations;  /* device [S,P,4] */
+    float *dL_dcov3D;      /* device [S,P,6] */
+} GsInGrads;
+
+/* Counters of the last forward on a context (host-visible after the call returns). */
+typedef struct GsStats {
+    int64_t num_rendered;  /* tile instances after culling (the "D" of SURVEY.md section 8(d)) */
+    int64_t num_visible;   /* Gaussians with radius > 0, summed over views */
+    int64_t saved_bytes;   /* bytes held by the GsSaved handle */
+    int64_t scratch_bytes; /* bytes of grow-only scratch held by the context */
+    int32_t kernel_launches; /* OUR kernels launched by the last forward (+ backward, if it followed); CUB's scan/sort launches are not counted */
+    int32_t reserved_;
+} GsStats;
+
+typedef struct GsContext GsContext; /* per (device, caller) workspace; not thread-safe, one call at a time */
+typedef struct GsSaved GsSaved;     /* state a forward keeps for its backward (what upstream hands autograd as 3 byte tensors) */
+
+GS_API int gs_abi_version(void);
+GS_API const char *gs_last_error(void);
+
+/* Workspace lifetime (upstream allocates scratch through torch callbacks on every call; here it is a grow-only cache). */
+GS_API int gs_context_create(GsContext **out);
+GS_API void gs_context_destroy(GsContext *ctx);
+
+/*
+ * Forward = _RasterizeGaussians.forward -> _C.rasterize_gaussians: preprocess,
+ * bin/sort, composite.  If `saved` is non-NULL a handle for gs_backward is returned (free it with
+ * gs_saved_free); pass NULL for inference.  Performs ONE host synchronisation per call (to size the tile
+ * instance list), like upstream does per view.
+ */
+GS_API int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *in, const GsOutputs *out, GsSaved **saved,
+               void *stream);
+
+/* Backward = _RasterizeGaussians.backward -> _C.rasterize_gaussians_backward. */
+GS_API int gs_backward(GsContext *ctx, const GsConfig *cfg, const GsInputs *in, const GsSaved *saved,
+                const GsOutGrads *gout, const GsInGrads *gin, void *stream);
+
+GS_API void gs_saved_free(GsContext *ctx, GsSaved *saved, void *stream);
+
+/* GaussianRasterizer.markVisible (unused by PF3plat; kept for surface completeness): present[V,P] = in frustum. */
+GS_API int gs_mark_visible(GsContext *ctx, const GsConfig *cfg, const float *means3D, uint8_t *present, void *stream);
+
+GS_API int gs_get_stats(const GsContext *ctx, GsStats *out);
+
+/*
+ * End-to-end entry with HOST buffers (what a non-torch plugin host calls): copies inputs to the device,
+ * renders, copies color/radii[/depth] back, and synchronises.  All pointers in cfg/in/out are HOST pointers
+ * here (pinned memory makes the copies asynchronous).  Forward only.
+ */
+GS_API int gs_render_host(GsContext *ctx, const GsConfig *cfg, const GsInputs *in, const GsOutputs *out, void *stream);
+
+/* Per-stage device timings (ms) of the last forward/backward when profiling is enabled; CUDA events on `stream`. */
+enum { GS_STAGE_PREPROCESS = 0, GS_STAGE_BIN = 1, GS_STAGE_COMPOSITE = 2, GS_STAGE_COMPOSITE_BWD = 3,
+       GS_STAGE_PREPROCESS_BWD = 4, GS_NUM_STAGES = 5 };
+GS_API int gs_set_profiling(GsContext *ctx, int enabled);
+GS_API int gs_get_stage_ms(GsContext *ctx, float *ms /* [GS_NUM_STAGES] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSPLAT_B200_H */

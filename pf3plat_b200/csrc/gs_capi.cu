@@ -1,0 +1,424 @@
+// gs_capi.cu -- the C ABI declared in include/gsplat_b200.h: argument validation, workspace management,
+// stage sequencing.  No torch, no exceptions across the boundary.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "gs_common.cuh"
+
+// ---------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+int gs_set_error(int code, const char *msg) {
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return code;
+}
+int gs_set_cuda_error(cudaError_t e, const char *what, const char *file, int line) {
+    snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+    return e == cudaErrorMemoryAllocation ? GS_ERR_OOM : GS_ERR_CUDA;
+}
+
+extern "C" const char *gs_last_error(void) { return g_err; }
+extern "C" int gs_abi_version(void) { return GS_ABI_VERSION; }
+
+// ---------------------------------------------------------------------------------------------------------
+// context: grow-only scratch, pinned read-back word, optional stage timers
+// ---------------------------------------------------------------------------------------------------------
+struct GrowBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t need, double headroom) {
+        if (need <= bytes) return GS_OK;
+        if (p) GS_CUDA_OK(cudaFree(p));  // implicit device sync: nothing in flight can still use it
+        p = nullptr;
+        bytes = 0;
+        size_t want = (size_t)((double)need * headroom) + 256;
+        GS_CUDA_OK(cudaMalloc(&p, want));
+        bytes = want;
+        return GS_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+struct GsContext {
+    GrowBuf per_gaussian;  // tiles_touched | offsets | rects | scan temp ; backward: accumulators
+    GrowBuf sort;          // keys_in | keys_out | vals_in | cub temp
+    GrowBuf host_stage;    // device mirror of host buffers (gs_render_host)
+    uint32_t *h_word = nullptr;  // pinned
+    GsStats stats{};
+    bool profiling = false;
+    cudaEvent_t ev[GS_NUM_STAGES + 1][2]{};
+    bool ev_valid[GS_NUM_STAGES] = {};
+    float stage_ms[GS_NUM_STAGES] = {};
+};
+
+namespace {
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct StageTimer {
+    GsContext *ctx;
+    int stage;
+    cudaStream_t st;
+    StageTimer(GsContext *c, int s, cudaStream_t stream) : ctx(c), stage(s), st(stream) {
+        if (ctx->profiling) cudaEventRecord(ctx->ev[stage][0], st);
+    }
+    ~StageTimer() {
+        if (ctx->profiling) {
+            cudaEventRecord(ctx->ev[stage][1], st);
+            ctx->ev_valid[stage] = true;
+        }
+    }
+};
+
+int validate(const GsConfig *cfg, const GsInputs *in) {
+    if (!cfg || !in) return gs_set_error(GS_ERR_INVALID, "null config/inputs");
+    if (cfg->P < 0 || cfg->S < 1 || cfg->V < 1 || cfg->V % cfg->S != 0)
+        return gs_set_error(GS_ERR_INVALID, "need P >= 0, S >= 1, V >= 1 and V % S == 0");
+    if (cfg->image_height < 1 || cfg->image_width < 1) return gs_set_error(GS_ERR_INVALID, "empty image");
+    if ((in->shs == nullptr) == (in->colors_precomp == nullptr) && cfg->P > 0)
+        return gs_set_error(GS_ERR_INVALID, "Please provide excatly one of either SHs or precomputed colors!");
+    const bool sr = in->scales != nullptr || in->rotations != nullptr;
+    if (cfg->P > 0 && ((sr && in->cov3D_precomp) || (!sr && !in->cov3D_precomp) ||
+                       (sr && (!in->scales || !in->rotations))))
+        return gs_set_error(GS_ERR_INVALID,
+                            "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+    if (in->shs && cfg->M < 1) return gs_set_error(GS_ERR_INVALID, "shs given but M < 1");
+    if (cfg->P > 0 && (!in->means3D || !in->opacities)) return gs_set_error(GS_ERR_INVALID, "means3D/opacities missing");
+    if (!cfg->viewmatrix || !cfg->projmatrix || !cfg->campos)
+        return gs_set_error(GS_ERR_INVALID, "viewmatrix/projmatrix/campos missing");
+    if ((int64_t)cfg->P * cfg->V > 0x7fffffffll) return gs_set_error(GS_ERR_OVERFLOW, "P*V exceeds 2^31-1");
+    if ((cfg->image_width + GS_TILE - 1) / GS_TILE > 65535 || (cfg->image_height + GS_TILE - 1) / GS_TILE > 65535)
+        return gs_set_error(GS_ERR_INVALID, "image too large");
+    return GS_OK;
+}
+
+DevCfg make_dev_cfg(const GsConfig *cfg) {
+    DevCfg c{};
+    c.P = cfg->P; c.S = cfg->S; c.V = cfg->V; c.VPS = cfg->V / cfg->S; c.M = cfg->M;
+    const int maxdeg = cfg->sh_eval_max_degree > 0 ? cfg->sh_eval_max_degree : 3;
+    int deg = cfg->sh_degree < maxdeg ? cfg->sh_degree : maxdeg;
+    if (deg > 3) deg = 3;                                    // the evaluator implements bands 0..3
+    while (deg > 0 && (deg + 1) * (deg + 1) > cfg->M) deg--;  // never read past the coefficients supplied
+    if (deg < 0) deg = 0;
+    c.deg = deg;
+    c.H = cfg->image_height; c.W = cfg->image_width;
+    c.gx = (c.W + GS_TILE - 1) / GS_TILE; c.gy = (c.H + GS_TILE - 1) / GS_TILE; c.ntiles = c.gx * c.gy;
+    c.flags = cfg->flags;
+    c.tanfovx = cfg->tanfovx; c.tanfovy = cfg->tanfovy; c.scale_modifier = cfg->scale_modifier;
+    c.near_cull_z = cfg->near_cull_z > 0.f ? cfg->near_cull_z : 0.2f;
+    c.dilation = cfg->dilation > 0.f ? cfg->dilation : 0.3f;
+    c.guard_band = cfg->guard_band > 0.f ? cfg->guard_band : 1.3f;
+    c.view = cfg->viewmatrix; c.proj = cfg->projmatrix; c.campos = cfg->campos; c.bg = cfg->bg;
+    c.tanfov = cfg->tanfov; c.view_scale = cfg->view_scale;
+    return c;
+}
+
+DevInputs make_dev_inputs(const GsInputs *in) {
+    DevInputs d{};
+    d.means3D = in->means3D; d.opacities = in->opacities; d.shs = in->shs; d.colors_precomp = in->colors_precomp;
+    d.scales = in->scales; d.rotations = in->rotations; d.cov3D = in->cov3D_precomp;
+    return d;
+}
+
+// carve the saved-state block (everything but the tile-instance list, which gets its own exactly-sized
+// allocation once its length has been read back)
+size_t saved_layout(GsSaved *s, const DevCfg &c, unsigned char *base) {
+    size_t off = 0;
+    const size_t n = (size_t)c.V * c.P, px = (size_t)c.V * c.H * c.W;
+    auto take = [&](size_t bytes) {
+        unsigned char *p = base ? base + off : nullptr;
+        off += align256(bytes);
+        return p;
+    };
+    s->rec0 = reinterpret_cast<float4 *>(take(n * 16));
+    s->rec1 = reinterpret_cast<float4 *>(take(n * 16));
+    s->rec2 = reinterpret_cast<float4 *>(take(n * 16));
+    s->meta = reinterpret_cast<uint8_t *>(take(n));
+    s->ranges = reinterpret_cast<uint2 *>(take((size_t)c.V * c.ntiles * 8));
+    s->final_T = reinterpret_cast<float *>(take(px * 4));
+    s->n_contrib = reinterpret_cast<uint32_t *>(take(px * 4));
+    return off;
+}
+
+}  // namespace
+
+extern "C" int gs_context_create(GsContext **out) {
+    if (!out) return gs_set_error(GS_ERR_INVALID, "null out");
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return gs_set_error(GS_ERR_NO_DEVICE, "no CUDA device");
+    GsContext *ctx = new (std::nothrow) GsContext();
+    if (!ctx) return gs_set_error(GS_ERR_OOM, "host allocation failed");
+    cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&ctx->h_word), 64);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return gs_set_cuda_error(e, "cudaMallocHost", __FILE__, __LINE__);
+    }
+    *out = ctx;
+    return GS_OK;
+}
+
+extern "C" void gs_context_destroy(GsContext *ctx) {
+    if (!ctx) return;
+    cudaDeviceSynchronize();
+    ctx->per_gaussian.release();
+    ctx->sort.release();
+    ctx->host_stage.release();
+    if (ctx->h_word) cudaFreeHost(ctx->h_word);
+    if (ctx->profiling)
+        for (auto &e : ctx->ev) {
+            if (e[0]) cudaEventDestroy(e[0]);
+            if (e[1]) cudaEventDestroy(e[1]);
+        }
+    delete ctx;
+}
+
+extern "C" int gs_set_profiling(GsContext *ctx, int enabled) {
+    if (!ctx) return gs_set_error(GS_ERR_INVALID, "null context");
+    if (enabled && !ctx->ev[0][0]) {
+        for (int s = 0; s < GS_NUM_STAGES; s++) {
+            GS_CUDA_OK(cudaEventCreate(&ctx->ev[s][0]));
+            GS_CUDA_OK(cudaEventCreate(&ctx->ev[s][1]));
+        }
+    }
+    ctx->profiling = enabled != 0;
+    return GS_OK;
+}
+
+extern "C" int gs_get_stage_ms(GsContext *ctx, float *ms) {
+    if (!ctx || !ms) return gs_set_error(GS_ERR_INVALID, "null argument");
+    for (int s = 0; s < GS_NUM_STAGES; s++) {
+        ms[s] = 0.f;
+        if (ctx->ev_valid[s]) {
+            GS_CUDA_OK(cudaEventSynchronize(ctx->ev[s][1]));
+            GS_CUDA_OK(cudaEventElapsedTime(&ms[s], ctx->ev[s][0], ctx->ev[s][1]));
+        }
+    }
+    return GS_OK;
+}
+
+extern "C" int gs_get_stats(const GsContext *ctx, GsStats *out) {
+    if (!ctx || !out) return gs_set_error(GS_ERR_INVALID, "null argument");
+    *out = ctx->stats;
+    out->scratch_bytes = (int64_t)(ctx->per_gaussian.bytes + ctx->sort.bytes + ctx->host_stage.bytes);
+    return GS_OK;
+}
+
+extern "C" void gs_saved_free(GsContext *ctx, GsSaved *saved, void *stream) {
+    (void)ctx;
+    if (!saved) return;
+    if (saved->point_list) cudaFreeAsync(saved->point_list, static_cast<cudaStream_t>(stream));
+    if (saved->base) cudaFreeAsync(saved->base, static_cast<cudaStream_t>(stream));
+    delete saved;
+}
+
+extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *in, const GsOutputs *out,
+                          GsSaved **saved_out, void *stream) {
+    if (saved_out) *saved_out = nullptr;
+    if (!ctx || !out) return gs_set_error(GS_ERR_INVALID, "null context/outputs");
+    int rc = validate(cfg, in);
+    if (rc != GS_OK) return rc;
+    if (!out->color || (cfg->P > 0 && !out->radii)) return gs_set_error(GS_ERR_INVALID, "color/radii outputs missing");
+    if ((cfg->flags & GS_FLAG_DEPTH) && !out->depth) return gs_set_error(GS_ERR_INVALID, "GS_FLAG_DEPTH needs out->depth");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const DevCfg c = make_dev_cfg(cfg);
+    const DevInputs di = make_dev_inputs(in);
+    const size_t n = (size_t)c.V * c.P;
+    for (bool &v : ctx->ev_valid) v = false;
+    ctx->stats.kernel_launches = 0;
+
+    // ---- per-Gaussian scratch: tiles_touched | offsets | rects | scan temp ----
+    const size_t scan_temp = bin_scan_temp_bytes((int64_t)n);
+    const size_t pg_bytes = 2 * align256(n * 4) + align256(n * 8) + scan_temp;
+    rc = ctx->per_gaussian.reserve(pg_bytes, 1.0);
+    if (rc != GS_OK) return rc;
+    unsigned char *pg = static_cast<unsigned char *>(ctx->per_gaussian.p);
+    uint32_t *tiles_touched = reinterpret_cast<uint32_t *>(pg);
+    uint32_t *offsets = reinterpret_cast<uint32_t *>(pg + align256(n * 4));
+    ushort4 *rects = reinterpret_cast<ushort4 *>(pg + 2 * align256(n * 4));
+    void *scan_tmp = pg + 2 * align256(n * 4) + align256(n * 8);
+
+    // ---- saved state: geometry / image planes now, the tile-instance list once its length is known ----
+    GsSaved *s = new (std::nothrow) GsSaved();
+    if (!s) return gs_set_error(GS_ERR_OOM, "host allocation failed");
+    memset(s, 0, sizeof(*s));
+    {
+        const size_t bytes = saved_layout(s, c, nullptr);
+        unsigned char *block = nullptr;
+        cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&block), bytes, st);
+        if (e != cudaSuccess) {
+            delete s;
+            return gs_set_cuda_error(e, "cudaMallocAsync(saved)", __FILE__, __LINE__);
+        }
+        saved_layout(s, c, block);
+        s->base = block;
+        s->bytes = bytes;
+    }
+    auto fail = [&](int code) {
+        gs_saved_free(ctx, s, stream);
+        return code;
+    };
+
+    {
+        StageTimer t(ctx, GS_STAGE_PREPROCESS, st);
+        rc = launch_preprocess(c, di, s->rec0, s->rec1, s->rec2, s->meta, out->radii, tiles_touched, rects, st);
+        if (rc != GS_OK) return fail(rc);
+        ctx->stats.kernel_launches += (c.P > 0);
+    }
+
+    int64_t D = 0;
+    {
+        StageTimer t(ctx, GS_STAGE_BIN, st);
+        if (n > 0) {
+            rc = bin_scan(c, tiles_touched, offsets, scan_tmp, scan_temp, st);
+            if (rc != GS_OK) return fail(rc);
+            cudaError_t e = cudaMemcpyAsync(ctx->h_word, offsets + (n - 1), 4, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the one host sync of the forward
+            if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "read back num_rendered", __FILE__, __LINE__));
+            D = (int64_t)*ctx->h_word;
+        }
+        if (D > 0x7fffffffll) return fail(gs_set_error(GS_ERR_OVERFLOW, "more than 2^31-1 tile instances"));
+        // the list lives in its own stream-ordered allocation (sized exactly)
+        cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&s->point_list), (size_t)(D > 0 ? D : 1) * 4, st);
+        if (e != cudaSuccess) {
+            s->point_list = nullptr;
+            return fail(gs_set_cuda_error(e, "cudaMallocAsync(point_list)", __FILE__, __LINE__));
+        }
+        s->D = D;
+        const size_t sort_bytes = bin_scratch_bytes(c, D);
+        rc = ctx->sort.reserve(sort_bytes, 1.25);
+        if (rc == GS_OK)
+            rc = bin_sort(c, D, s->rec2, tiles_touched, rects, offsets, ctx->sort.p, ctx->sort.bytes, s->point_list,
+                          s->ranges, st);
+        if (rc != GS_OK) return fail(rc);
+        ctx->stats.kernel_launches += D > 0 ? 2 : 0;  // k_duplicate, k_ranges (CUB's scan/sort launches not counted)
+    }
+
+    {
+        StageTimer t(ctx, GS_STAGE_COMPOSITE, st);
+        rc = launch_composite_fwd(c, *s, out->color, out->depth, st);
+        if (rc != GS_OK) return fail(rc);
+        ctx->stats.kernel_launches += 1;
+    }
+
+    s->P = c.P; s->S = c.S; s->V = c.V; s->H = c.H; s->W = c.W;
+    s->flags = c.flags;
+    s->has_sh = in->shs != nullptr;
+    s->has_scales = in->scales != nullptr;
+    ctx->stats.num_rendered = D;
+    ctx->stats.num_visible = -1;
+    ctx->stats.saved_bytes = (int64_t)(s->bytes + (size_t)(D > 0 ? D : 1) * 4);
+    if (saved_out) {
+        *saved_out = s;
+    } else {
+        gs_saved_free(ctx, s, stream);
+    }
+    return GS_OK;
+}
+
+extern "C" int gs_backward(GsContext *ctx, const GsConfig *cfg, const GsInputs *in, const GsSaved *saved,
+                           const GsOutGrads *gout, const GsInGrads *gin, void *stream) {
+    if (!ctx || !saved || !gout || !gin) return gs_set_error(GS_ERR_INVALID, "null argument");
+    int rc = validate(cfg, in);
+    if (rc != GS_OK) return rc;
+    if (!gout->dL_dcolor) return gs_set_error(GS_ERR_INVALID, "dL_dcolor missing");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DevCfg c = make_dev_cfg(cfg);
+    if (saved->P != c.P || saved->V != c.V || saved->S != c.S || saved->H != c.H || saved->W != c.W)
+        return gs_set_error(GS_ERR_INVALID, "saved state does not match the configuration");
+    c.flags = saved->flags;
+    const DevInputs di = make_dev_inputs(in);
+    const size_t n = (size_t)c.V * c.P;
+    if (n == 0) return GS_OK;
+
+    rc = ctx->per_gaussian.reserve(n * GS_ACC_STRIDE * 4, 1.0);
+    if (rc != GS_OK) return rc;
+    float *acc = static_cast<float *>(ctx->per_gaussian.p);
+    {
+        StageTimer t(ctx, GS_STAGE_COMPOSITE_BWD, st);
+        GS_CUDA_OK(cudaMemsetAsync(acc, 0, n * GS_ACC_STRIDE * 4, st));
+        rc = launch_composite_bwd(c, *saved, gout->dL_dcolor, gout->dL_ddepth, acc, st);
+        if (rc != GS_OK) return rc;
+    }
+    {
+        StageTimer t(ctx, GS_STAGE_PREPROCESS_BWD, st);
+        rc = launch_preprocess_bwd(c, di, *saved, acc, *gin, st);
+        if (rc != GS_OK) return rc;
+    }
+    ctx->stats.kernel_launches += 2;  // k_composite_bwd, k_preprocess_bwd
+    return GS_OK;
+}
+
+extern "C" int gs_mark_visible(GsContext *ctx, const GsConfig *cfg, const float *means3D, uint8_t *present,
+                               void *stream) {
+    if (!ctx || !cfg || !means3D || !present) return gs_set_error(GS_ERR_INVALID, "null argument");
+    if (cfg->S < 1 || cfg->V < 1 || cfg->V % cfg->S != 0 || !cfg->viewmatrix)
+        return gs_set_error(GS_ERR_INVALID, "bad configuration");
+    DevCfg c = make_dev_cfg(cfg);
+    return launch_mark_visible(c, means3D, present, static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// end-to-end entry with host buffers
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int gs_render_host(GsContext *ctx, const GsConfig *cfg, const GsInputs *in, const GsOutputs *out,
+                              void *stream) {
+    if (!ctx || !out) return gs_set_error(GS_ERR_INVALID, "null context/outputs");
+    int rc = validate(cfg, in);
+    if (rc != GS_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t SP = (size_t)cfg->S * cfg->P, VP = (size_t)cfg->V * cfg->P, V = (size_t)cfg->V;
+    const size_t px = V * cfg->image_height * cfg->image_width;
+    struct Item { const void *h; size_t bytes; const void **d; };
+    GsConfig dc = *cfg;
+    GsInputs din{};
+    GsOutputs dout{};
+    Item items[] = {
+        {cfg->viewmatrix, V * 64, (const void **)&dc.viewmatrix},
+        {cfg->projmatrix, V * 64, (const void **)&dc.projmatrix},
+        {cfg->campos, V * 12, (const void **)&dc.campos},
+        {cfg->bg, cfg->bg ? V * 12 : 0, (const void **)&dc.bg},
+        {cfg->tanfov, cfg->tanfov ? V * 8 : 0, (const void **)&dc.tanfov},
+        {cfg->view_scale, cfg->view_scale ? V * 4 : 0, (const void **)&dc.view_scale},
+        {in->means3D, SP * 12, (const void **)&din.means3D},
+        {in->opacities, SP * 4, (const void **)&din.opacities},
+        {in->shs, in->shs ? SP * cfg->M * 12 : 0, (const void **)&din.shs},
+        {in->colors_precomp, in->colors_precomp ? VP * 12 : 0, (const void **)&din.colors_precomp},
+        {in->scales, in->scales ? SP * 12 : 0, (const void **)&din.scales},
+        {in->rotations, in->rotations ? SP * 16 : 0, (const void **)&din.rotations},
+        {in->cov3D_precomp, in->cov3D_precomp ? SP * 24 : 0, (const void **)&din.cov3D_precomp},
+    };
+    size_t total = 0;
+    for (const Item &it : items) total += align256(it.bytes);
+    const size_t out_off = total;
+    total += align256(px * 12) + align256(VP * 4) + align256(px * 4);
+    rc = ctx->host_stage.reserve(total, 1.0);
+    if (rc != GS_OK) return rc;
+    unsigned char *base = static_cast<unsigned char *>(ctx->host_stage.p);
+    size_t off = 0;
+    for (const Item &it : items) {
+        *it.d = nullptr;
+        if (it.bytes) {
+            *it.d = base + off;
+            GS_CUDA_OK(cudaMemcpyAsync(base + off, it.h, it.bytes, cudaMemcpyHostToDevice, st));
+        }
+        off += align256(it.bytes);
+    }
+    dout.color = reinterpret_cast<float *>(base + out_off);
+    dout.radii = reinterpret_cast<int32_t *>(base + out_off + align256(px * 12));
+    dout.depth = (cfg->flags & GS_FLAG_DEPTH) ? reinterpret_cast<float *>(base + out_off + align256(px * 12) + align256(VP * 4))
+                                              : nullptr;
+    rc = gs_forward(ctx, &dc, &din, &dout, nullptr, stream);
+    if (rc != GS_OK) return rc;
+    if (out->color) GS_CUDA_OK(cudaMemcpyAsync(out->color, dout.color, px * 12, cudaMemcpyDeviceToHost, st));
+    if (out->radii && VP) GS_CUDA_OK(cudaMemcpyAsync(out->radii, dout.radii, VP * 4, cudaMemcpyDeviceToHost, st));
+    if (out->depth && dout.depth) GS_CUDA_OK(cudaMemcpyAsync(out->depth, dout.depth, px * 4, cudaMemcpyDeviceToHost, st));
+    GS_CUDA_OK(cudaStreamSynchronize(st));
+    return GS_OK;
+}

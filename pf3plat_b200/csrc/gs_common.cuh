@@ -1,0 +1,273 @@
+// gs_common.cuh -- shared device/host declarations of the sm_100a splatting kernels.
+//
+// Data layout in HBM.  Per (view, Gaussian) "splat record", three float4 SoA planes of
+// V*P entries each, written by preprocess and gathered by the compositors with 16-byte loads:
+//   rec0 = (x_pix, y_pix, -0.5*log2e*conic_a, -log2e*conic_b)
+//   rec1 = (-0.5*log2e*conic_c, opacity, r, g)
+//   rec2 = (b, z_cam, hx, hy)         hx,hy = half extents of the alpha >= 1/255 ellipse's bounding box
+// The conic is stored pre-scaled so that the compositors get log2(G) = power*log2(e) with five FP ops and feed
+// it straight to ex2.approx (gs_power2 / gs_ex2 below; forward and backward share them bit for bit).
+// plus meta[V*P] (uint8: bits 0-2 = SH clamp flags, bit 3 = visible).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gsplat_b200.h"
+
+#define GS_TILE 16
+#define GS_TILE_PX (GS_TILE * GS_TILE)
+
+#define GS_META_VISIBLE 8u
+
+struct DevCfg {
+    int P, S, V, VPS, M, deg, H, W, gx, gy, ntiles;
+    uint32_t flags;
+    float tanfovx, tanfovy, scale_modifier, near_cull_z, dilation, guard_band;
+    const float *view, *proj, *campos, *bg, *tanfov, *view_scale;
+};
+
+struct DevInputs {
+    const float *means3D, *opacities, *shs, *colors_precomp, *scales, *rotations, *cov3D;
+};
+
+// State a forward keeps for its backward; one stream-ordered allocation carved into planes.
+struct GsSaved {
+    void *base;
+    size_t bytes;
+    float4 *rec0, *rec1, *rec2;   // [V*P]
+    uint8_t *meta;                // [V*P]
+    uint32_t *point_list;         // [D] Gaussian index within its scene, per tile in (depth, index) order
+    uint2 *ranges;                // [V*ntiles] [start,end) into point_list
+    float *final_T;               // [V*H*W]
+    uint32_t *n_contrib;          // [V*H*W] 1-based list position of the last contributor
+    int64_t D;
+    int P, S, V, H, W;
+    uint32_t flags;
+    int has_sh, has_scales;
+};
+
+#define GS_CUDA_OK(call)                                                             \
+    do {                                                                             \
+        cudaError_t e_ = (call);                                                     \
+        if (e_ != cudaSuccess) return gs_set_cuda_error(e_, #call, __FILE__, __LINE__); \
+    } while (0)
+
+int gs_set_cuda_error(cudaError_t e, const char *what, const char *file, int line);
+int gs_set_error(int code, const char *msg);
+
+// ---- kernel launchers (one translation unit per stage) ----
+int launch_preprocess(const DevCfg &c, const DevInputs &in, float4 *rec0, float4 *rec1, float4 *rec2, uint8_t *meta,
+                      int32_t *radii, uint32_t *tiles_touched, ushort4 *rects, cudaStream_t st);
+int launch_mark_visible(const DevCfg &c, const float *means3D, uint8_t *present, cudaStream_t st);
+
+size_t bin_scratch_bytes(const DevCfg &c, int64_t D);
+int bin_scan(const DevCfg &c, const uint32_t *tiles_touched, uint32_t *offsets, void *temp, size_t temp_bytes,
+             cudaStream_t st);
+size_t bin_scan_temp_bytes(int64_t n);
+int bin_sort(const DevCfg &c, int64_t D, const float4 *rec2, const uint32_t *tiles_touched, const ushort4 *rects,
+             const uint32_t *offsets, void *scratch, size_t scratch_bytes, uint32_t *point_list, uint2 *ranges,
+             cudaStream_t st);
+
+int launch_composite_fwd(const DevCfg &c, const GsSaved &s, float *color, float *depth, cudaStream_t st);
+int launch_composite_bwd(const DevCfg &c, const GsSaved &s, const float *dL_dcolor, const float *dL_ddepth,
+                         float *grad_acc /* [V*P*GS_ACC_STRIDE], zeroed */, cudaStream_t st);
+int launch_preprocess_bwd(const DevCfg &c, const DevInputs &in, const GsSaved &s, const float *grad_acc,
+                          const GsInGrads &g, cudaStream_t st);
+
+// per (view,Gaussian) accumulator written by the composite backward:
+//   0-2 dL/drgb, 3-4 dL/dmean2D (NDC-scaled), 5-7 dL/dconic (a, b stored once, c), 8 dL/dopacity, 9 dL/dz
+#define GS_ACC_STRIDE 10
+
+// ---------------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// Column-major flat (transposed) 4x4 times point; the explicit fma chain matches oracle/gs_oracle.c so the
+// camera-space depth (the sort key) is bit-identical on both sides.
+__device__ __forceinline__ float3 xform4x3(const float *__restrict__ m, float3 p) {
+    float3 o;
+    o.x = fmaf(m[0], p.x, fmaf(m[4], p.y, fmaf(m[8], p.z, m[12])));
+    o.y = fmaf(m[1], p.x, fmaf(m[5], p.y, fmaf(m[9], p.z, m[13])));
+    o.z = fmaf(m[2], p.x, fmaf(m[6], p.y, fmaf(m[10], p.z, m[14])));
+    return o;
+}
+__device__ __forceinline__ float4 xform4x4(const float *__restrict__ m, float3 p) {
+    float4 o;
+    o.x = fmaf(m[0], p.x, fmaf(m[4], p.y, fmaf(m[8], p.z, m[12])));
+    o.y = fmaf(m[1], p.x, fmaf(m[5], p.y, fmaf(m[9], p.z, m[13])));
+    o.z = fmaf(m[2], p.x, fmaf(m[6], p.y, fmaf(m[10], p.z, m[14])));
+    o.w = fmaf(m[3], p.x, fmaf(m[7], p.y, fmaf(m[11], p.z, m[15])));
+    return o;
+}
+__device__ __forceinline__ float ndc2pix(float v, int S) { return ((v + 1.0f) * (float)S - 1.0f) * 0.5f; }
+
+// Camera block of one view, staged in shared memory by every kernel that needs it.
+struct ViewCam {
+    float view[16];
+    float proj[16];
+    float campos[3];
+    float tanfovx, tanfovy, scale;
+    float bg[3];
+};
+
+__device__ __forceinline__ void load_view_cam(const DevCfg &c, int v, ViewCam *cam) {
+    // called by all threads of the block; followed by __syncthreads() at the call site
+    int t = threadIdx.x + threadIdx.y * blockDim.x;
+    if (t < 16) {
+        cam->view[t] = c.view[v * 16 + t];
+        cam->proj[t] = c.proj[v * 16 + t];
+    } else if (t < 19) {
+        cam->campos[t - 16] = c.campos[v * 3 + (t - 16)];
+    } else if (t < 22) {
+        cam->bg[t - 19] = c.bg ? c.bg[v * 3 + (t - 19)] : 0.0f;
+    } else if (t == 22) {
+        cam->tanfovx = c.tanfov ? c.tanfov[v * 2 + 0] : c.tanfovx;
+        cam->tanfovy = c.tanfov ? c.tanfov[v * 2 + 1] : c.tanfovy;
+        cam->scale = c.view_scale ? c.view_scale[v] : 1.0f;
+    }
+}
+
+// Projection Jacobian rows m0,m1 of M = J * Rview and the clamp masks (oracle build_jac).
+struct ProjJac {
+    float m0[3], m1[3];
+    float tx, ty, tz, fx, fy;
+    bool xin, yin;
+};
+
+__device__ __forceinline__ void build_jac(const ViewCam &cam, const DevCfg &c, float3 mean, ProjJac &o) {
+    float3 t = xform4x3(cam.view, mean);
+    const float limx = c.guard_band * cam.tanfovx, limy = c.guard_band * cam.tanfovy;
+    const float txtz = t.x / t.z, tytz = t.y / t.z;
+    o.xin = !(txtz < -limx || txtz > limx);
+    o.yin = !(tytz < -limy || tytz > limy);
+    t.x = fminf(limx, fmaxf(-limx, txtz)) * t.z;
+    t.y = fminf(limy, fmaxf(-limy, tytz)) * t.z;
+    o.fx = (float)c.W / (2.0f * cam.tanfovx);
+    o.fy = (float)c.H / (2.0f * cam.tanfovy);
+    const float J00 = o.fx / t.z, J02 = -(o.fx * t.x) / (t.z * t.z);
+    const float J11 = o.fy / t.z, J12 = -(o.fy * t.y) / (t.z * t.z);
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        o.m0[j] = J00 * cam.view[j * 4 + 0] + J02 * cam.view[j * 4 + 2];
+        o.m1[j] = J11 * cam.view[j * 4 + 1] + J12 * cam.view[j * 4 + 2];
+    }
+    o.tx = t.x; o.ty = t.y; o.tz = t.z;
+}
+
+__device__ __forceinline__ void sym6_mul(const float *c6, const float *v, float *o) {
+    o[0] = c6[0] * v[0] + c6[1] * v[1] + c6[2] * v[2];
+    o[1] = c6[1] * v[0] + c6[3] * v[1] + c6[4] * v[2];
+    o[2] = c6[2] * v[0] + c6[4] * v[1] + c6[5] * v[2];
+}
+
+__device__ __forceinline__ void quat_to_R(const float *q, float R[3][3]) {
+    const float r = q[0], x = q[1], y = q[2], z = q[3];
+    R[0][0] = 1.f - 2.f * (y * y + z * z); R[0][1] = 2.f * (x * y - r * z); R[0][2] = 2.f * (x * z + r * y);
+    R[1][0] = 2.f * (x * y + r * z); R[1][1] = 1.f - 2.f * (x * x + z * z); R[1][2] = 2.f * (y * z - r * x);
+    R[2][0] = 2.f * (x * z - r * y); R[2][1] = 2.f * (y * z + r * x); R[2][2] = 1.f - 2.f * (x * x + y * y);
+}
+
+// Sigma = R diag((mod*s)^2) R^T
+__device__ __forceinline__ void cov3d_from_scale_rot(const float *s, float mod, const float *q, float *c6) {
+    float R[3][3];
+    quat_to_R(q, R);
+    const float v0 = mod * s[0] * mod * s[0], v1 = mod * s[1] * mod * s[1], v2 = mod * s[2] * mod * s[2];
+    c6[0] = R[0][0] * v0 * R[0][0] + R[0][1] * v1 * R[0][1] + R[0][2] * v2 * R[0][2];
+    c6[1] = R[0][0] * v0 * R[1][0] + R[0][1] * v1 * R[1][1] + R[0][2] * v2 * R[1][2];
+    c6[2] = R[0][0] * v0 * R[2][0] + R[0][1] * v1 * R[2][1] + R[0][2] * v2 * R[2][2];
+    c6[3] = R[1][0] * v0 * R[1][0] + R[1][1] * v1 * R[1][1] + R[1][2] * v2 * R[1][2];
+    c6[4] = R[1][0] * v0 * R[2][0] + R[1][1] * v1 * R[2][1] + R[1][2] * v2 * R[2][2];
+    c6[5] = R[2][0] * v0 * R[2][0] + R[2][1] * v1 * R[2][1] + R[2][2] * v2 * R[2][2];
+}
+
+#define GS_LOG2E 1.4426950408889634f
+#define GS_ALPHA_MIN (1.0f / 255.0f)
+#define GS_ALPHA_MAX 0.99f
+#define GS_T_MIN 0.0001f
+
+// log2 of the Gaussian falloff at offset (dx,dy) from the centre, from the pre-scaled conic in rec0/rec1.
+// Explicit round-to-nearest intrinsics: no re-association or contraction, so the forward and backward
+// compositors take identical skip decisions.
+__device__ __forceinline__ float gs_power2(float hA, float nB, float hC, float dx, float dy) {
+    const float t1 = __fmaf_rn(hA, dx, __fmul_rn(nB, dy));
+    const float t2 = __fmul_rn(hC, dy);
+    return __fmaf_rn(dx, t1, __fmul_rn(dy, t2));
+}
+__device__ __forceinline__ float gs_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+#define GS_SH_C0 0.28209479177387814f
+#define GS_SH_C1 0.4886025119029199f
+#define GS_SH_C2_0 1.0925484305920792f
+#define GS_SH_C2_1 (-1.0925484305920792f)
+#define GS_SH_C2_2 0.31539156525252005f
+#define GS_SH_C2_3 (-1.0925484305920792f)
+#define GS_SH_C2_4 0.5462742152960396f
+#define GS_SH_C3_0 (-0.5900435899266435f)
+#define GS_SH_C3_1 2.890611442640554f
+#define GS_SH_C3_2 (-0.4570457994644658f)
+#define GS_SH_C3_3 0.3731763325901154f
+#define GS_SH_C3_4 (-0.4570457994644658f)
+#define GS_SH_C3_5 1.445305721320277f
+#define GS_SH_C3_6 (-0.5900435899266435f)
+
+// ---- mbarrier + 1-D bulk TMA (cp.async.bulk) primitives ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+}
+// global -> shared bulk copy (TMA engine, SASS UBLKCP); bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global bulk store
+__device__ __forceinline__ void tma_store_1d(void *gdst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 16-byte cp.async (LDGSTS) gather used by the compositors' producer warp
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// arrive on an mbarrier once all of this thread's prior cp.async have landed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,216 @@
+// gs_composite_bwd.cu -- stage 1 of the backward: per-pixel reverse walk, gradients scattered to per-(view,
+// Gaussian) accumulators.
+//
+// Semantics: SURVEY.md Appendix A "Composite backward" (upstream renderCUDA backward): starting at the last
+// contributor, recompute alpha, T <- T/(1-alpha), and accumulate dL/d{colour, mean2D, conic, opacity}; the
+// gradient passes straight through the 0.99 clamp; the conic's off-diagonal term is stored once.
+//
+// B200 design.  Same CTA/warp/pixel mapping and the same ballot culling as the forward
+// (so both walk identical survivor sets).  Upstream issues 9 global float atomics per (pixel, Gaussian) pair;
+// here the 32 pixel lanes of a warp keep their 10 partial gradients for up to THREE Gaussians in registers
+// (30 values + 2 pads), a 31-shuffle butterfly transposes-and-reduces them so that lane L ends up holding the
+// warp total of value L, and ONE red.global.add.f32 instruction with 30 distinct addresses retires them:
+// ~10 shuffles and one atomic instruction per Gaussian per warp instead of 45 shuffles or 288 atomics.
+#include "gs_common.cuh"
+
+namespace {
+
+constexpr int CB_THREADS = 256;
+constexpr int CB_BATCH = 256;
+constexpr int CB_GROUP = 3;  // Gaussians reduced per butterfly (3 * GS_ACC_STRIDE = 30 <= 32)
+
+// After this, lane L holds the sum over all 32 lanes of the caller's v[L].
+__device__ __forceinline__ float butterfly_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; i++) {
+            const float send = upper ? v[i] : v[i + s];
+            const float keep = upper ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
+
+// Per-pixel state of the reverse walk.
+struct PixState {
+    float T, T_final, last_alpha;
+    float accum[3], last_color[3];
+    float accum_d, last_d;
+    float dLp[3], dLd, bg_dot;
+    uint32_t last;  // number of list entries this pixel walked up to its last contributor
+};
+
+template <bool DEPTH>
+__device__ __forceinline__ void pixel_grad(PixState &ps, bool live, float4 q0, float4 q1, float4 q2, float pxf,
+                                           float pyf, float half_w, float half_h, float *g /* [GS_ACC_STRIDE] */) {
+#pragma unroll
+    for (int k = 0; k < GS_ACC_STRIDE; k++) g[k] = 0.f;
+    if (!live) return;
+    const float dx = q0.x - pxf, dy = q0.y - pyf;
+    const float p2 = gs_power2(q0.z, q0.w, q1.x, dx, dy);
+    if (p2 > 0.0f) return;
+    const float G = gs_ex2(p2);
+    const float alpha = fminf(GS_ALPHA_MAX, q1.y * G);
+    if (alpha < GS_ALPHA_MIN) return;
+    ps.T = ps.T / (1.0f - alpha);
+    const float w = alpha * ps.T;
+    const float col[3] = {q1.z, q1.w, q2.x};
+    float dL_dalpha = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+        ps.accum[ch] = ps.last_alpha * ps.last_color[ch] + (1.0f - ps.last_alpha) * ps.accum[ch];
+        ps.last_color[ch] = col[ch];
+        dL_dalpha += (col[ch] - ps.accum[ch]) * ps.dLp[ch];
+        g[ch] = w * ps.dLp[ch];
+    }
+    if (DEPTH) {
+        ps.accum_d = ps.last_alpha * ps.last_d + (1.0f - ps.last_alpha) * ps.accum_d;
+        ps.last_d = q2.y;
+        dL_dalpha += (q2.y - ps.accum_d) * ps.dLd;
+        g[9] = w * ps.dLd;
+    }
+    dL_dalpha *= ps.T;
+    ps.last_alpha = alpha;
+    dL_dalpha += (-ps.T_final / (1.0f - alpha)) * ps.bg_dot;
+    const float dL_dG = q1.y * dL_dalpha;  // straight through the 0.99 clamp
+    // true conic from the pre-scaled record: A = hA * (-2/log2e), B = nB * (-1/log2e)
+    const float A = q0.z * (-2.0f / GS_LOG2E), B = q0.w * (-1.0f / GS_LOG2E), Cc = q1.x * (-2.0f / GS_LOG2E);
+    const float gdx = G * dx, gdy = G * dy;
+    const float dG_ddelx = -gdx * A - gdy * B;
+    const float dG_ddely = -gdy * Cc - gdx * B;
+    g[3] = dL_dG * dG_ddelx * half_w;
+    g[4] = dL_dG * dG_ddely * half_h;
+    g[5] = -0.5f * gdx * dx * dL_dG;
+    g[6] = -0.5f * gdx * dy * dL_dG;
+    g[7] = -0.5f * gdy * dy * dL_dG;
+    g[8] = G * dL_dalpha;
+}
+
+template <bool DEPTH>
+__global__ void __launch_bounds__(CB_THREADS)
+k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *__restrict__ rec1,
+                const float4 *__restrict__ rec2, const uint32_t *__restrict__ point_list,
+                const uint2 *__restrict__ ranges, const float *__restrict__ final_T,
+                const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dcolor,
+                const float *__restrict__ dL_ddepth, float *__restrict__ acc) {
+    __shared__ float4 s0[CB_BATCH], s1[CB_BATCH], s2[CB_BATCH];
+    __shared__ uint32_t sid[CB_BATCH];
+    __shared__ uint32_t s_max[CB_THREADS / 32];
+
+    const int v = blockIdx.y;
+    const int tile = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int bx = (tile % c.gx) * GS_TILE + (warp & 1) * 8;
+    const int by = (tile / c.gx) * GS_TILE + (warp >> 1) * 4;
+    const int px = bx + (lane & 7), py = by + (lane >> 3);
+    const bool inside = px < c.W && py < c.H;
+    const float pxf = (float)px, pyf = (float)py;
+    const float bx0 = (float)bx, bx1 = (float)(bx + 7), by0 = (float)by, by1 = (float)(by + 3);
+    const float half_w = 0.5f * (float)c.W, half_h = 0.5f * (float)c.H;
+
+    const uint2 range = ranges[(size_t)v * c.ntiles + tile];
+    const size_t rbase = (size_t)v * c.P;
+    const size_t hw = (size_t)c.H * c.W;
+    const size_t pix = (size_t)py * c.W + px;
+
+    PixState ps;
+    ps.last = 0;
+    ps.T_final = 1.f;
+    ps.dLp[0] = ps.dLp[1] = ps.dLp[2] = 0.f;
+    ps.dLd = 0.f;
+    if (inside) {
+        ps.last = n_contrib[(size_t)v * hw + pix];
+        ps.T_final = final_T[(size_t)v * hw + pix];
+        const float *dl = dL_dcolor + (size_t)v * 3 * hw + pix;
+        ps.dLp[0] = dl[0];
+        ps.dLp[1] = dl[hw];
+        ps.dLp[2] = dl[2 * hw];
+        if (DEPTH && dL_ddepth) ps.dLd = dL_ddepth[(size_t)v * hw + pix];
+    }
+    ps.T = ps.T_final;
+    ps.last_alpha = 0.f;
+    ps.accum_d = ps.last_d = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) ps.accum[ch] = ps.last_color[ch] = 0.f;
+    const float *bg = c.bg ? c.bg + (size_t)v * 3 : nullptr;
+    ps.bg_dot = bg ? bg[0] * ps.dLp[0] + bg[1] * ps.dLp[1] + bg[2] * ps.dLp[2] : 0.f;
+
+    // the walk starts at the deepest position any pixel of the tile reached
+    const uint32_t warp_last = __reduce_max_sync(0xffffffffu, ps.last);
+    if (lane == 0) s_max[warp] = warp_last;
+    __syncthreads();
+    uint32_t cta_last = 0;
+#pragma unroll
+    for (int w = 0; w < CB_THREADS / 32; w++) cta_last = max(cta_last, s_max[w]);
+
+    for (uint32_t hi = cta_last; hi > 0; hi -= min(hi, (uint32_t)CB_BATCH)) {
+        const uint32_t lo = hi > CB_BATCH ? hi - CB_BATCH : 0u;  // list positions [lo, hi), relative to range.x
+        const uint32_t nb = hi - lo;
+        __syncthreads();  // previous batch fully consumed
+        if ((uint32_t)tid < nb) {
+            const uint32_t id = point_list[range.x + lo + tid];
+            const size_t r = rbase + id;
+            sid[tid] = id;
+            s0[tid] = rec0[r];
+            s1[tid] = rec1[r];
+            s2[tid] = rec2[r];
+        }
+        __syncthreads();
+        if (lo >= warp_last) continue;  // nothing in this batch is below any of this warp's last contributors
+        for (int chunk = (int)((nb - 1) & ~31u); chunk >= 0; chunk -= 32) {
+            const uint32_t j = (uint32_t)chunk + lane;
+            bool hit = false;
+            if (j < nb && lo + j < warp_last) {
+                const float4 a = s0[j], e = s2[j];
+                hit = (a.x + e.z >= bx0) && (a.x - e.z <= bx1) && (a.y + e.w >= by0) && (a.y - e.w <= by1);
+            }
+            uint32_t mask = __ballot_sync(0xffffffffu, hit);
+            while (mask) {
+                float gv[32];
+                uint32_t gid[CB_GROUP];
+#pragma unroll
+                for (int slot = 0; slot < CB_GROUP; slot++) {
+                    float *g = gv + slot * GS_ACC_STRIDE;
+                    if (mask) {
+                        const int b = 31 - __clz(mask);  // deepest first
+                        mask &= ~(1u << b);
+                        const uint32_t jj = (uint32_t)chunk + b;
+                        gid[slot] = sid[jj];
+                        pixel_grad<DEPTH>(ps, lo + jj < ps.last, s0[jj], s1[jj], s2[jj], pxf, pyf, half_w, half_h, g);
+                    } else {
+                        gid[slot] = 0xffffffffu;
+#pragma unroll
+                        for (int k = 0; k < GS_ACC_STRIDE; k++) g[k] = 0.f;
+                    }
+                }
+                gv[30] = gv[31] = 0.f;
+                const float total = butterfly_reduce32(gv, lane);
+                const int slot = lane / GS_ACC_STRIDE, comp = lane - slot * GS_ACC_STRIDE;
+                uint32_t id = gid[0];
+                if (slot == 1) id = gid[1];
+                if (slot == 2) id = gid[2];
+                if (lane < CB_GROUP * GS_ACC_STRIDE && id != 0xffffffffu && total != 0.0f)
+                    atomicAdd(acc + (rbase + id) * GS_ACC_STRIDE + comp, total);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+int launch_composite_bwd(const DevCfg &c, const GsSaved &s, const float *dL_dcolor, const float *dL_ddepth,
+                         float *grad_acc, cudaStream_t st) {
+    if (c.V == 0 || c.ntiles == 0) return GS_OK;
+    dim3 grid(c.ntiles, c.V);
+    if (c.flags & GS_FLAG_DEPTH)
+        k_composite_bwd<true><<<grid, CB_THREADS, 0, st>>>(c, s.rec0, s.rec1, s.rec2, s.point_list, s.ranges, s.final_T,
+                                                          s.n_contrib, dL_dcolor, dL_ddepth, grad_acc);
+    else
+        k_composite_bwd<false><<<grid, CB_THREADS, 0, st>>>(c, s.rec0, s.rec1, s.rec2, s.point_list, s.ranges,
+                                                           s.final_T, s.n_contrib, dL_dcolor, dL_ddepth, grad_acc);
+    GS_CUDA_OK(cudaGetLastError());
+    return GS_OK;
+}

@@ -1,0 +1,256 @@
+// gs_preprocess.cu -- stage 1 of the forward: per (view, Gaussian) projection, culling, 2-D conic, SH colour.
+//
+// Semantics: SURVEY.md Appendix A "Preprocess" (the external extension's preprocessCUDA; call site
+// /root/reference/src/model/decoder/cuda_splatting.py:117-124).  B200 design:
+//  * one thread per Gaussian, LOOPING over the views of its scene, so the scene-level inputs (mean, covariance
+//    and the 300-byte SH block) are read from HBM once per call instead of once per view;
+//  * the CTA's contiguous SH block is staged into shared memory by ONE 1-D bulk TMA copy (cp.async.bulk,
+//    SASS UBLKCP) completing on an mbarrier -- fully coalesced, no register staging;
+//  * outputs are three float4 SoA planes written with 16-byte stores;
+//  * tile binning uses the bounding box of the alpha >= 1/255 ellipse intersected with upstream's 3-sigma
+//    square, so tile lists only hold Gaussians that can actually contribute (identical pixels, fewer pairs).
+#include "gs_common.cuh"
+
+namespace {
+
+constexpr int PRE_THREADS = 128;
+
+struct PreSmem {
+    ViewCam cam;
+    uint64_t bar;
+};
+
+__device__ __forceinline__ float3 eval_sh(int deg, const float *sh /* [M][3] for this Gaussian */, float3 dir,
+                                          uint32_t &clamped) {
+    const float x = dir.x, y = dir.y, z = dir.z;
+    float r[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        float v = GS_SH_C0 * sh[0 * 3 + c];
+        if (deg > 0) {
+            v = v - GS_SH_C1 * y * sh[1 * 3 + c] + GS_SH_C1 * z * sh[2 * 3 + c] - GS_SH_C1 * x * sh[3 * 3 + c];
+            if (deg > 1) {
+                const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                v = v + GS_SH_C2_0 * xy * sh[4 * 3 + c] + GS_SH_C2_1 * yz * sh[5 * 3 + c] +
+                    GS_SH_C2_2 * (2.0f * zz - xx - yy) * sh[6 * 3 + c] + GS_SH_C2_3 * xz * sh[7 * 3 + c] +
+                    GS_SH_C2_4 * (xx - yy) * sh[8 * 3 + c];
+                if (deg > 2) {
+                    v = v + GS_SH_C3_0 * y * (3.0f * xx - yy) * sh[9 * 3 + c] + GS_SH_C3_1 * xy * z * sh[10 * 3 + c] +
+                        GS_SH_C3_2 * y * (4.0f * zz - xx - yy) * sh[11 * 3 + c] +
+                        GS_SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[12 * 3 + c] +
+                        GS_SH_C3_4 * x * (4.0f * zz - xx - yy) * sh[13 * 3 + c] +
+                        GS_SH_C3_5 * z * (xx - yy) * sh[14 * 3 + c] + GS_SH_C3_6 * x * (xx - 3.0f * yy) * sh[15 * 3 + c];
+                }
+            }
+        }
+        v += 0.5f;
+        if (v < 0.0f) clamped |= (1u << c);
+        r[c] = fmaxf(v, 0.0f);
+    }
+    return make_float3(r[0], r[1], r[2]);
+}
+
+// Everything preprocess derives for one (view, Gaussian).
+struct Splat {
+    float4 r0, r1, r2;
+    int32_t radius;
+    uint32_t tiles, meta;
+    ushort4 rect;
+};
+
+// Appendix A "Preprocess" for one Gaussian in one view.  `sh` points at this Gaussian's [M][3] block in shared
+// memory (HAS_SH) ; `rgb_in` is its precomputed colour otherwise.
+template <bool HAS_SH>
+__device__ __forceinline__ void project_splat(const DevCfg &c, const ViewCam &cam, float3 mean, const float *c6,
+                                              float opac, const float *sh, const float *rgb_in, Splat &out) {
+    out.radius = 0;
+    out.tiles = 0;
+    out.meta = 0;
+    out.rect = make_ushort4(0, 0, 0, 0);
+    const float s = cam.scale, s2 = s * s;
+    const float3 m = make_float3(mean.x * s, mean.y * s, mean.z * s);
+    const float3 pv = xform4x3(cam.view, m);
+    if (!(pv.z > c.near_cull_z)) return;  // in_frustum
+    const float4 ph = xform4x4(cam.proj, m);
+    const float pw = 1.0f / (ph.w + 0.0000001f);
+    const float cv[6] = {c6[0] * s2, c6[1] * s2, c6[2] * s2, c6[3] * s2, c6[4] * s2, c6[5] * s2};
+    ProjJac j;
+    build_jac(cam, c, m, j);
+    float s0[3], s1[3];
+    sym6_mul(cv, j.m0, s0);
+    sym6_mul(cv, j.m1, s1);
+    const float a = j.m0[0] * s0[0] + j.m0[1] * s0[1] + j.m0[2] * s0[2] + c.dilation;
+    const float b = j.m0[0] * s1[0] + j.m0[1] * s1[1] + j.m0[2] * s1[2];
+    const float cc = j.m1[0] * s1[0] + j.m1[1] * s1[1] + j.m1[2] * s1[2] + c.dilation;
+    const float det = a * cc - b * b;
+    if (det == 0.0f) return;
+    const float det_inv = 1.0f / det;
+    const float A = cc * det_inv, B = -b * det_inv, C = a * det_inv;
+    const float mid = 0.5f * (a + cc);
+    const float sq = sqrtf(fmaxf(0.1f, mid * mid - det));
+    const float rad = ceilf(3.0f * sqrtf(fmaxf(mid + sq, mid - sq)));
+    const float px = ndc2pix(ph.x * pw, c.W), py = ndc2pix(ph.y * pw, c.H);
+    // upstream's 3-sigma square in tiles (getRect)
+    const int rminx = min(c.gx, max(0, (int)((px - rad) / (float)GS_TILE)));
+    const int rminy = min(c.gy, max(0, (int)((py - rad) / (float)GS_TILE)));
+    const int rmaxx = min(c.gx, max(0, (int)((px + rad + (float)(GS_TILE - 1)) / (float)GS_TILE)));
+    const int rmaxy = min(c.gy, max(0, (int)((py + rad + (float)(GS_TILE - 1)) / (float)GS_TILE)));
+    if ((rmaxx - rminx) * (rmaxy - rminy) == 0) return;
+    out.radius = (int32_t)rad;
+    out.meta = GS_META_VISIBLE;
+    float3 rgb;
+    if (HAS_SH) {
+        float3 d = make_float3(m.x - cam.campos[0], m.y - cam.campos[1], m.z - cam.campos[2]);
+        const float inv = 1.0f / sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+        d.x *= inv; d.y *= inv; d.z *= inv;
+        rgb = eval_sh(c.deg, sh, d, out.meta);
+    } else {
+        rgb = make_float3(rgb_in[0], rgb_in[1], rgb_in[2]);
+    }
+    // Tight binning.  A pixel can only receive this Gaussian if alpha = o*exp(-q/2) >= 1/255, i.e. inside the
+    // ellipse q = d^T Q d <= tau = 2 ln(255 o).  Its bounding box has half extents sqrt(tau * Qinv_ii); tiles
+    // outside it (or outside upstream's square) cannot change any pixel, so they are not binned.  tau carries a
+    // margin for the fp32 rounding of q in the compositor (grows with the reach of the footprint), and the
+    // determinant is taken in fp64 from the fp32 conic actually used by the compositor.
+    float hx = 0.f, hy = 0.f;
+    const float reach = rad + (float)GS_TILE;
+    const float tau = 2.0f * logf(255.0f * opac) + 1e-3f + 4e-6f * reach * reach;
+    if (tau > 0.0f) {
+        const double dq = (double)A * (double)C - (double)B * (double)B;
+        if (dq > 0.0) {
+            hx = (float)sqrt((double)tau * (double)C / dq) * 1.0001f + 1e-3f;
+            hy = (float)sqrt((double)tau * (double)A / dq) * 1.0001f + 1e-3f;
+        } else {
+            hx = hy = 3.0e38f;
+        }
+        const float k = 1.0f / (float)GS_TILE;
+        const float fx0 = floorf((px - hx) * k), fx1 = floorf((px + hx) * k);
+        const float fy0 = floorf((py - hy) * k), fy1 = floorf((py + hy) * k);
+        const int tx0 = max(rminx, (int)fmaxf(fx0, 0.0f)), ty0 = max(rminy, (int)fmaxf(fy0, 0.0f));
+        const int tx1 = fx1 < 0.0f ? 0 : min(rmaxx, (int)fminf(fx1, 65534.0f) + 1);
+        const int ty1 = fy1 < 0.0f ? 0 : min(rmaxy, (int)fminf(fy1, 65534.0f) + 1);
+        if (tx1 > tx0 && ty1 > ty0) {
+            out.tiles = (uint32_t)(tx1 - tx0) * (uint32_t)(ty1 - ty0);
+            out.rect = make_ushort4((unsigned short)tx0, (unsigned short)ty0, (unsigned short)tx1, (unsigned short)ty1);
+        }
+    }
+    out.r0 = make_float4(px, py, (-0.5f * GS_LOG2E) * A, -GS_LOG2E * B);
+    out.r1 = make_float4((-0.5f * GS_LOG2E) * C, opac, rgb.x, rgb.y);
+    out.r2 = make_float4(rgb.z, pv.z, hx, hy);
+}
+
+template <bool HAS_SH>
+__global__ void __launch_bounds__(PRE_THREADS)
+k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, float4 *__restrict__ rec1,
+             float4 *__restrict__ rec2, uint8_t *__restrict__ meta, int32_t *__restrict__ radii,
+             uint32_t *__restrict__ tiles_touched, ushort4 *__restrict__ rects) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    PreSmem *sm = reinterpret_cast<PreSmem *>(smem_raw);
+    float *sh_s = reinterpret_cast<float *>(smem_raw + 256);  // PreSmem fits in 256 bytes
+
+    const int scene = blockIdx.y;
+    const int g0 = blockIdx.x * PRE_THREADS;
+    const int n = min(PRE_THREADS, c.P - g0);
+    const int tid = threadIdx.x;
+    const int i = g0 + tid;
+    const bool active = tid < n;
+    const size_t sg = (size_t)scene * c.P + i;  // scene-level index
+
+    // ---- stage this CTA's SH block (n * M * 3 contiguous floats) with one bulk TMA copy ----
+    bool bulk = false;
+    if (HAS_SH) {
+        const float *src = in.shs + ((size_t)scene * c.P + g0) * c.M * 3;
+        const uint32_t bytes = (uint32_t)n * c.M * 12u;
+        bulk = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && ((bytes & 15u) == 0);
+        if (bulk) {
+            if (tid == 0) {
+                mbar_init(&sm->bar, 1);
+                mbar_fence_init();
+                mbar_expect_tx(&sm->bar, bytes);
+                tma_load_1d(sh_s, src, bytes, &sm->bar);
+            }
+        } else {  // unaligned slice or ragged tail: plain coalesced copy
+            for (uint32_t k = tid; k < (uint32_t)n * c.M * 3u; k += PRE_THREADS) sh_s[k] = src[k];
+        }
+    }
+    // ---- scene-level inputs (issued while the bulk copy is in flight) ----
+    float3 mean = make_float3(0, 0, 0);
+    float c6[6] = {0, 0, 0, 0, 0, 0};
+    float opac = 0.f;
+    if (active) {
+        mean = make_float3(in.means3D[sg * 3 + 0], in.means3D[sg * 3 + 1], in.means3D[sg * 3 + 2]);
+        opac = in.opacities[sg];
+        if (in.cov3D) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) c6[k] = in.cov3D[sg * 6 + k];
+        } else {
+            const float s[3] = {in.scales[sg * 3 + 0], in.scales[sg * 3 + 1], in.scales[sg * 3 + 2]};
+            const float q[4] = {in.rotations[sg * 4 + 0], in.rotations[sg * 4 + 1], in.rotations[sg * 4 + 2],
+                                in.rotations[sg * 4 + 3]};
+            cov3d_from_scale_rot(s, c.scale_modifier, q, c6);
+        }
+    }
+    if (HAS_SH) {
+        __syncthreads();  // barrier init (bulk) or the copy loop (fallback) visible to everyone
+        if (bulk) mbar_wait(&sm->bar, 0);
+    }
+
+    for (int vi = 0; vi < c.VPS; vi++) {
+        const int v = scene * c.VPS + vi;
+        __syncthreads();
+        load_view_cam(c, v, &sm->cam);
+        __syncthreads();
+        if (!active) continue;
+        const size_t o = (size_t)v * c.P + i;
+        Splat sp;
+        project_splat<HAS_SH>(c, sm->cam, mean, c6, opac, sh_s + (size_t)tid * c.M * 3,
+                              HAS_SH ? nullptr : in.colors_precomp + o * 3, sp);
+        if (sp.radius > 0) {
+            rec0[o] = sp.r0;
+            rec1[o] = sp.r1;
+            rec2[o] = sp.r2;
+        }
+        radii[o] = sp.radius;
+        tiles_touched[o] = sp.tiles;
+        rects[o] = sp.rect;
+        meta[o] = (uint8_t)sp.meta;
+    }
+}
+
+__global__ void k_mark_visible(const DevCfg c, const float *__restrict__ means3D, uint8_t *__restrict__ present) {
+    __shared__ ViewCam cam;
+    const int v = blockIdx.y;
+    load_view_cam(c, v, &cam);
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.P) return;
+    const size_t sg = (size_t)(v / c.VPS) * c.P + i;
+    const float s = cam.scale;
+    const float3 m = make_float3(means3D[sg * 3] * s, means3D[sg * 3 + 1] * s, means3D[sg * 3 + 2] * s);
+    present[(size_t)v * c.P + i] = xform4x3(cam.view, m).z > c.near_cull_z;
+}
+
+}  // namespace
+
+int launch_preprocess(const DevCfg &c, const DevInputs &in, float4 *rec0, float4 *rec1, float4 *rec2, uint8_t *meta,
+                      int32_t *radii, uint32_t *tiles_touched, ushort4 *rects, cudaStream_t st) {
+    if (c.P == 0) return GS_OK;
+    dim3 grid((c.P + PRE_THREADS - 1) / PRE_THREADS, c.S);
+    if (in.shs) {
+        size_t smem = 256 + (size_t)PRE_THREADS * c.M * 12;
+        GS_CUDA_OK(cudaFuncSetAttribute(k_preprocess<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_preprocess<true><<<grid, PRE_THREADS, smem, st>>>(c, in, rec0, rec1, rec2, meta, radii, tiles_touched, rects);
+    } else {
+        k_preprocess<false><<<grid, PRE_THREADS, 256, st>>>(c, in, rec0, rec1, rec2, meta, radii, tiles_touched, rects);
+    }
+    GS_CUDA_OK(cudaGetLastError());
+    return GS_OK;
+}
+
+int launch_mark_visible(const DevCfg &c, const float *means3D, uint8_t *present, cudaStream_t st) {
+    if (c.P == 0) return GS_OK;
+    dim3 grid((c.P + 255) / 256, c.V);
+    k_mark_visible<<<grid, 256, 0, st>>>(c, means3D, present);
+    GS_CUDA_OK(cudaGetLastError());
+    return GS_OK;
+}

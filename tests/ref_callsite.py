@@ -1,0 +1,64 @@
+"""Line-by-line restatement of how PF3plat calls the rasterizer (the reference tree is absent on the GPU box, so
+the GPU tests cannot import it).  Mirrors /root/reference/src/model/decoder/cuda_splatting.py:47-127
+(`render_cuda`): 1/near rescale, SH relayout, fov/projection, and the PER-VIEW loop that builds
+GaussianRasterizationSettings with `.item()` floats, a zero `means2D` that requires grad, and
+`cov[:, row, col]` from `torch.triu_indices`.  The CPU test
+tests/test_capi_cpu.py::test_reference_render_glue_imports_and_reaches_our_operator_unmodified drives the real file."""
+from math import isqrt
+
+import torch
+from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+
+from pf3plat_b200.cameras import get_fov, get_projection_matrix
+
+
+def render_like_reference(extrinsics, intrinsics, near, far, image_shape, background_color, gaussian_means,
+                          gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, scale_invariant=True,
+                          use_sh=True, return_radii=False, return_means2d=False):
+    assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
+    if scale_invariant:
+        scale = 1 / near
+        extrinsics = extrinsics.clone()
+        extrinsics[..., :3, 3] = extrinsics[..., :3, 3] * scale[:, None]
+        gaussian_covariances = gaussian_covariances * (scale[:, None, None, None] ** 2)
+        gaussian_means = gaussian_means * scale[:, None, None]
+        near = near * scale
+        far = far * scale
+    _, _, _, n = gaussian_sh_coefficients.shape
+    degree = isqrt(n) - 1
+    shs = gaussian_sh_coefficients.permute(0, 1, 3, 2).contiguous()
+    b, _, _ = extrinsics.shape
+    h, w = image_shape
+    fov_x, fov_y = get_fov(intrinsics).unbind(dim=-1)
+    tan_fov_x = (0.5 * fov_x).tan()
+    tan_fov_y = (0.5 * fov_y).tan()
+    projection_matrix = get_projection_matrix(near, far, fov_x, fov_y).transpose(-1, -2)
+    view_matrix = extrinsics.inverse().transpose(-1, -2)
+    full_projection = view_matrix @ projection_matrix
+    all_images, all_radii, all_m2d = [], [], []
+    for i in range(b):
+        mean_gradients = torch.zeros_like(gaussian_means[i], requires_grad=True)
+        try:
+            mean_gradients.retain_grad()
+        except Exception:
+            pass
+        settings = GaussianRasterizationSettings(
+            image_height=h, image_width=w, tanfovx=tan_fov_x[i].item(), tanfovy=tan_fov_y[i].item(),
+            bg=background_color[i], scale_modifier=1.0, viewmatrix=view_matrix[i], projmatrix=full_projection[i],
+            sh_degree=degree, campos=extrinsics[i, :3, 3], prefiltered=False, debug=False)
+        rasterizer = GaussianRasterizer(settings)
+        row, col = torch.triu_indices(3, 3)
+        image, radii = rasterizer(
+            means3D=gaussian_means[i], means2D=mean_gradients, shs=shs[i] if use_sh else None,
+            colors_precomp=None if use_sh else shs[i, :, 0, :], opacities=gaussian_opacities[i, ..., None],
+            cov3D_precomp=gaussian_covariances[i, :, row, col])
+        all_images.append(image)
+        all_radii.append(radii)
+        all_m2d.append(mean_gradients)
+    out = torch.stack(all_images)
+    extra = []
+    if return_radii:
+        extra.append(torch.stack(all_radii))
+    if return_means2d:
+        extra.append(all_m2d)
+    return (out, *extra) if extra else out

@@ -1,0 +1,139 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads without a GPU and exports every symbol
+include/gsplat_b200.h declares; the ctypes mirrors match the C struct layouts; the Python operator surface has
+the reference's names, fields and error behaviour.  No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "gsplat_b200.h")
+
+
+@pytest.fixture(scope="module")
+def capi():
+    import __graft_entry__ as ge
+    ge.build()
+    from pf3plat_b200 import _capi
+    return _capi
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    return re.findall(r"GS_API\s+[\w\s\*]+?\b(gs_\w+)\s*\(", src)
+
+
+def test_library_loads_and_exports_every_declared_symbol(capi):
+    L = capi.lib()
+    declared = _declared_functions()
+    assert len(declared) >= 12
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/gsplat_b200.h but not exported"
+        assert name in capi.SYMBOLS, f"{name} has no ctypes prototype"
+    assert set(capi.SYMBOLS) == set(declared)
+    assert L.gs_abi_version() == capi.ABI_VERSION
+
+
+def test_ctypes_struct_layouts_match_the_header(capi, tmp_path):
+    names = ["GsConfig", "GsInputs", "GsOutputs", "GsOutGrads", "GsInGrads", "GsStats"]
+    prog = tmp_path / "sizes.c"
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "gsplat_b200.h"\nint main(void){'
+                    + "".join(f'printf("%zu\\n", sizeof({n}));' for n in names)
+                    + 'printf("%zu\\n", offsetof(GsConfig, viewmatrix));printf("%zu\\n", offsetof(GsConfig, tanfovx));'
+                    + "return 0;}")
+    exe = tmp_path / "sizes"
+    subprocess.run(["/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc", "-I", os.path.join(ROOT, "include"),
+                    str(prog), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    for n, sz in zip(names, out):
+        assert ctypes.sizeof(getattr(capi, n)) == int(sz), n
+    assert capi.GsConfig.viewmatrix.offset == int(out[len(names)])
+    assert capi.GsConfig.tanfovx.offset == int(out[len(names) + 1])
+
+
+def test_null_arguments_are_rejected_without_a_device(capi):
+    L = capi.lib()
+    assert L.gs_forward(None, None, None, None, None, None) == -1
+    assert b"null" in L.gs_last_error()
+    assert L.gs_backward(None, None, None, None, None, None, None) == -1
+    assert L.gs_get_stats(None, None) == -1
+    L.gs_saved_free(None, None, None)      # no-op
+    L.gs_context_destroy(None)             # no-op
+
+
+def test_operator_surface_matches_the_reference_call_site():
+    import diff_gaussian_rasterization as dgr
+    from pf3plat_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+    assert dgr.GaussianRasterizer is GaussianRasterizer
+    # the 12 fields, keyword-constructible exactly as in cuda_splatting.py:99-112
+    s = dgr.GaussianRasterizationSettings(
+        image_height=8, image_width=8, tanfovx=0.5, tanfovy=0.5, bg=torch.zeros(3), scale_modifier=1.0,
+        viewmatrix=torch.eye(4), projmatrix=torch.eye(4), sh_degree=4, campos=torch.zeros(3), prefiltered=False,
+        debug=False)
+    assert s._fields == ("image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix",
+                         "projmatrix", "sh_degree", "campos", "prefiltered", "debug")
+    r = dgr.GaussianRasterizer(s)
+    assert isinstance(r, torch.nn.Module) and hasattr(r, "markVisible")
+    P = 4
+    kw = dict(means3D=torch.zeros(P, 3), means2D=torch.zeros(P, 3), opacities=torch.ones(P, 1))
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        r(**kw, cov3D_precomp=torch.zeros(P, 6))
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair or precomputed 3D covariance"):
+        r(**kw, shs=torch.zeros(P, 25, 3))
+    # CPU tensors: the product path refuses loudly instead of falling back
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        r(**kw, shs=torch.zeros(P, 25, 3), cov3D_precomp=torch.zeros(P, 6))
+
+
+def test_product_code_never_touches_the_oracle():
+    bad = []
+    for pkg in ("pf3plat_b200", "diff_gaussian_rasterization"):
+        for dp, _, fs in os.walk(os.path.join(ROOT, pkg)):
+            for f in fs:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
+                    txt = open(os.path.join(dp, f)).read()
+                    if re.search(r"(from|import)\s+oracle|oracle/gs_oracle|libgs_oracle", txt) and "oracle/gs_oracle.c" not in txt:
+                        bad.append(os.path.join(dp, f))
+                    elif re.search(r"^\s*(from|import)\s+oracle", txt, re.M):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad
+
+
+REF = "/root/reference/src/model/decoder/cuda_splatting.py"
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference tree only exists in the build container")
+def test_reference_render_glue_imports_and_reaches_our_operator_unmodified():
+    """Imports the reference's cuda_splatting.py UNMODIFIED against this repo's `diff_gaussian_rasterization`
+    and drives render_cuda with CPU tensors: all of the reference's own glue runs and the call arrives at our
+    operator, which refuses CPU tensors loudly.  (The same call pattern is exercised on the GPU by
+    tests/test_gpu_dropin.py through a line-by-line restatement, since /root/reference is absent there.)"""
+    import importlib.util
+    import types
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k == "src" or k.startswith("src.")}
+    try:
+        for name in ("src", "src.model", "src.model.decoder", "src.model.encoder", "src.model.encoder.costvolume",
+                     "src.geometry"):
+            m = types.ModuleType(name)
+            m.__path__ = [os.path.join("/root/reference", *name.split("."))]
+            sys.modules[name] = m
+        spec = importlib.util.spec_from_file_location("src.model.decoder.cuda_splatting", REF)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[spec.name] = mod
+        spec.loader.exec_module(mod)
+        from pf3plat_b200.synthetic import make_scene
+        sc = make_scene(64, 2, 32, 32)
+        rep = lambda t: t[None].expand(2, *t.shape)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            mod.render_cuda(sc.extrinsics, sc.intrinsics, sc.near, sc.far, sc.image_shape, sc.background,
+                            rep(sc.means), rep(sc.covariances), rep(sc.harmonics), rep(sc.opacities))
+    finally:
+        for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+            del sys.modules[k]
+        for k, v in saved.items():
+            if v is not None:
+                sys.modules[k] = v
