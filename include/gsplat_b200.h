@@ -56,6 +56,10 @@ enum {
     GS_FLAG_PREFILTERED = 2u   /* GaussianRasterizationSettings.prefiltered */
 };
 
+enum {
+    GS_TUNE_FORCE_RADIX_BINNING = 1u /* use the device-wide radix-sort binning even when every tile list fits shared memory */
+};
+
 /* GaussianRasterizationSettings (cuda_splatting.py:99-112), batched over views. */
 typedef struct GsConfig {
     int32_t P;            /* Gaussians per scene */
@@ -74,7 +78,7 @@ typedef struct GsConfig {
     float dilation;       /* default 0.3 */
     float guard_band;     /* default 1.3 */
     int32_t sh_eval_max_degree; /* default 3 (<=0 selects it) */
-    int32_t reserved_;
+    uint32_t tuning;      /* GS_TUNE_* implementation knobs (testing); 0 = default */
     const float *viewmatrix; /* device [V,16]  settings.viewmatrix */
     const float *projmatrix; /* device [V,16]  settings.projmatrix */
     const float *campos;     /* device [V,3]   settings.campos */
@@ -129,7 +133,7 @@ typedef struct GsStats {
     int64_t saved_bytes;   /* bytes held by the GsSaved handle */
     int64_t scratch_bytes; /* bytes of grow-only scratch held by the context */
     int32_t kernel_launches; /* OUR kernels launched by the last forward (+ backward, if it followed); CUB's scan/sort launches are not counted */
-    int32_t reserved_;
+    int32_t max_tile_list;   /* longest (view, tile) list of the last forward */
 } GsStats;
 
 typedef struct GsContext GsContext; /* per (device, caller) workspace; not thread-safe, one call at a time */

@@ -16,6 +16,7 @@ ABI_VERSION = 1
 
 GS_FLAG_DEPTH = 1
 GS_FLAG_PREFILTERED = 2
+GS_TUNE_FORCE_RADIX_BINNING = 1
 GS_NUM_STAGES = 5
 STAGE_NAMES = ("preprocess", "bin", "composite", "composite_bwd", "preprocess_bwd")
 
@@ -26,7 +27,7 @@ class GsConfig(Structure):
         ("image_height", c_int32), ("image_width", c_int32), ("flags", c_uint32),
         ("tanfovx", c_float), ("tanfovy", c_float), ("scale_modifier", c_float),
         ("near_cull_z", c_float), ("dilation", c_float), ("guard_band", c_float),
-        ("sh_eval_max_degree", c_int32), ("reserved_", c_int32),
+        ("sh_eval_max_degree", c_int32), ("tuning", c_uint32),
         ("viewmatrix", c_void_p), ("projmatrix", c_void_p), ("campos", c_void_p), ("bg", c_void_p),
         ("tanfov", c_void_p), ("view_scale", c_void_p),
     ]
@@ -53,7 +54,7 @@ class GsInGrads(Structure):
 
 class GsStats(Structure):
     _fields_ = [("num_rendered", c_int64), ("num_visible", c_int64), ("saved_bytes", c_int64),
-                ("scratch_bytes", c_int64), ("kernel_launches", c_int32), ("reserved_", c_int32)]
+                ("scratch_bytes", c_int64), ("kernel_launches", c_int32), ("max_tile_list", c_int32)]
 
 
 # every symbol include/gsplat_b200.h declares: name -> (restype, argtypes)

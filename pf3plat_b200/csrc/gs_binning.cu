@@ -1,98 +1,280 @@
 // gs_binning.cu -- stage 2 of the forward: per-tile lists of Gaussians in (depth, index) order.
 //
-// Semantics: SURVEY.md Appendix A "Binning" (upstream K2-K5).  All views of the call are binned by ONE
-// scan / sort: the key is ((view * tiles + tile) << 32) | fp32 bits of camera-space depth, the value the
-// Gaussian's index in its scene; a stable LSD radix sort then orders every tile by (depth, index) exactly as
-// upstream's emission-order + stable sort does.  Only key bits [0, 32 + log2(V * tiles)) are sorted.
-// The scan and the radix sort are CUB library calls (library code, like cuBLAS for a plain GEMM); the
-// duplicate/range kernels are ours.  DESIGN.md section 5.2 has the traffic accounting.
+// Semantics: SURVEY.md Appendix A "Binning" (upstream K2-K5): every (view, tile) list holds the Gaussians whose
+// footprint touches the tile, ordered by fp32 depth bits, ties by Gaussian index.  Upstream gets that order from
+// ONE device-wide radix sort of 64-bit (tile | depth) keys over all D tile instances: ~6 passes of 12-byte pairs.
+//
+// B200 design, all views of the call at once.
+//  FAST PATH (every tile list fits one CTA's shared memory, <= BIN_SMEM_CAP entries):
+//    1. preprocess already counted the instances per (view, tile) with global reductions (RED.ADD).  Same-sector
+//       atomics serialise in L2 (measured: ~57 ns per op and address with 2k hot words), so every tile has
+//       BIN_SUB sub-counters, chosen by the Gaussian's index, each alone in its 32-byte sector;
+//    2. k_tile_scan: one CTA turns the counters into sub-bucket offsets, the total D and the longest list;
+//    3. k_emit_buckets: every Gaussian appends (depth_bits << 32 | index) to its sub-bucket of each tile it
+//       touches (atomic cursor per sub-bucket; the arrival order is arbitrary).  A tile's sub-buckets are
+//       contiguous, so together they are the tile's bucket;
+//    4. k_tile_sort: one CTA per (view, tile) loads its bucket into registers/shared memory, merge-sorts the
+//       64-bit keys -- a total order, so the arbitrary arrival order does not matter -- and writes the index list
+//       and the tile's [start, end) range.
+//    HBM traffic: 8 B written + 8 B read + 4 B written per instance, one pass each (vs ~6 x 24 B upstream).
+//  FALLBACK (some list longer than BIN_SMEM_CAP, or forced through GsConfig.tuning): two-level device-wide radix
+//    sort -- Gaussians by depth (64-bit keys, bits [32,64)), instances emitted in that order and sorted stably
+//    by (view, tile) only.
+// The block-level merge sort, the device scan and the device radix sorts are CUB primitives (library code, like
+// cuBLAS for a plain GEMM); the count / scan / emit / range kernels are ours.
 #include <cub/cub.cuh>
 
 #include "gs_common.cuh"
 
 namespace {
 
-__global__ void k_duplicate(const DevCfg c, const float4 *__restrict__ rec2, const uint32_t *__restrict__ tiles_touched,
-                            const ushort4 *__restrict__ rects, const uint32_t *__restrict__ offsets,
-                            uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t n = (size_t)c.V * c.P;
-    if (idx >= n) return;
-    if (tiles_touched[idx] == 0) return;
-    uint32_t off = idx == 0 ? 0u : offsets[idx - 1];
-    const int v = (int)(idx / c.P);
-    const uint32_t i = (uint32_t)(idx - (size_t)v * c.P);
-    const ushort4 r = rects[idx];
-    const uint32_t dbits = __float_as_uint(rec2[idx].y);
-    const uint32_t tbase = (uint32_t)v * (uint32_t)c.ntiles;
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// ---------------------------------------------------------------------------------------------------------
+// fast path
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 1024;
+
+// counters[nvt * BIN_SUB] (padded: one per 32-byte sector) -> exclusive sub-bucket offsets[nvt * BIN_SUB],
+// per-tile totals tile_n[nvt], tile starts tile_start[nvt]; info[0] = total, info[1] = longest tile list
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_tile_scan(int nvt, const uint32_t *__restrict__ counters, uint32_t *__restrict__ offsets,
+            uint32_t *__restrict__ tile_start, uint32_t *__restrict__ tile_n, uint32_t *__restrict__ info) {
+    using BlockScan = cub::BlockScan<uint32_t, SCAN_THREADS>;
+    using BlockReduce = cub::BlockReduce<uint32_t, SCAN_THREADS>;
+    __shared__ union {
+        typename BlockScan::TempStorage scan;
+        typename BlockReduce::TempStorage reduce;
+    } tmp;
+    const int per = (nvt + SCAN_THREADS - 1) / SCAN_THREADS;  // tiles per thread
+    const int b = threadIdx.x * per, e = min(nvt, b + per);
+    uint32_t sum = 0, mx = 0;
+    for (int t = b; t < e; t++) {
+        uint32_t tn = 0;
+#pragma unroll
+        for (int k = 0; k < BIN_SUB; k++) tn += counters[((size_t)t * BIN_SUB + k) * BIN_PAD];
+        sum += tn;
+        mx = max(mx, tn);
+    }
+    uint32_t excl, total;
+    BlockScan(tmp.scan).ExclusiveSum(sum, excl, total);
+    __syncthreads();
+    const uint32_t bmax = BlockReduce(tmp.reduce).Reduce(mx, cub::Max());
+    for (int t = b; t < e; t++) {
+        tile_start[t] = excl;
+        uint32_t tn = 0;
+#pragma unroll
+        for (int k = 0; k < BIN_SUB; k++) {
+            offsets[(size_t)t * BIN_SUB + k] = excl + tn;
+            tn += counters[((size_t)t * BIN_SUB + k) * BIN_PAD];
+        }
+        tile_n[t] = tn;
+        excl += tn;
+    }
+    if (threadIdx.x == 0) {
+        info[0] = total;
+        info[1] = bmax;
+    }
+}
+
+__global__ void k_emit_buckets(const DevCfg c, const float4 *__restrict__ rec2, const ushort4 *__restrict__ rects,
+                               const uint32_t *__restrict__ offsets, uint32_t *__restrict__ cursor,
+                               uint64_t *__restrict__ bucket) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (size_t)c.V * c.P) return;
+    const ushort4 r = rects[g];
+    if (r.z <= r.x || r.w <= r.y) return;
+    const uint32_t v = (uint32_t)(g / c.P);
+    const uint32_t i = (uint32_t)(g - (size_t)v * c.P);
+    const uint64_t key = ((uint64_t)__float_as_uint(rec2[g].y) << 32) | i;
+    const uint32_t tbase = v * (uint32_t)c.ntiles;
+    const uint32_t sub = i & (BIN_SUB - 1);
     for (int y = r.y; y < r.w; y++)
         for (int x = r.x; x < r.z; x++) {
-            keys[off] = ((uint64_t)(tbase + (uint32_t)(y * c.gx + x)) << 32) | dbits;
+            const size_t slot = (size_t)(tbase + (uint32_t)(y * c.gx + x)) * BIN_SUB + sub;
+            const uint32_t pos = atomicAdd(&cursor[slot * BIN_PAD], 1u);
+            bucket[(size_t)offsets[slot] + pos] = key;
+        }
+}
+
+constexpr int TS_THREADS = 256;
+
+template <int ITEMS>
+__device__ __forceinline__ void sort_bucket(const uint64_t *__restrict__ src, uint32_t *__restrict__ dst, uint32_t n,
+                                            void *smem) {
+    using Sort = cub::BlockMergeSort<uint64_t, TS_THREADS, ITEMS>;
+    typename Sort::TempStorage &tmp = *reinterpret_cast<typename Sort::TempStorage *>(smem);
+    uint64_t keys[ITEMS];
+    const uint32_t base = threadIdx.x * ITEMS;
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) keys[k] = base + k < n ? src[base + k] : ~0ull;
+    Sort(tmp).Sort(keys, [](const uint64_t &a, const uint64_t &b) { return a < b; });
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++)
+        if (base + k < n) dst[base + k] = (uint32_t)keys[k];
+}
+
+template <int MAX_ITEMS>
+__global__ void __launch_bounds__(TS_THREADS)
+k_tile_sort(const uint32_t *__restrict__ tile_n, const uint32_t *__restrict__ tile_start,
+            const uint64_t *__restrict__ bucket, uint32_t *__restrict__ point_list, uint2 *__restrict__ ranges) {
+    extern __shared__ __align__(16) unsigned char ts_smem[];
+    const uint32_t vt = blockIdx.x;
+    const uint32_t n = tile_n[vt], off = tile_start[vt];
+    if (threadIdx.x == 0) ranges[vt] = make_uint2(off, off + n);
+    if (n == 0) return;
+    const uint64_t *src = bucket + off;
+    uint32_t *dst = point_list + off;
+    if (n <= TS_THREADS * 2) sort_bucket<2>(src, dst, n, ts_smem);
+    else if (MAX_ITEMS >= 8 && n <= TS_THREADS * 8) sort_bucket<(MAX_ITEMS >= 8 ? 8 : 2)>(src, dst, n, ts_smem);
+    else if (MAX_ITEMS >= 16 && n <= TS_THREADS * 16) sort_bucket<(MAX_ITEMS >= 16 ? 16 : 2)>(src, dst, n, ts_smem);
+    else sort_bucket<MAX_ITEMS>(src, dst, n, ts_smem);
+}
+
+template <int MAX_ITEMS>
+int launch_tile_sort(int nvt, const uint32_t *counts, const uint32_t *offsets, const uint64_t *bucket,
+                     uint32_t *point_list, uint2 *ranges, cudaStream_t st) {
+    const size_t smem = sizeof(typename cub::BlockMergeSort<uint64_t, TS_THREADS, MAX_ITEMS>::TempStorage);
+    GS_CUDA_OK(cudaFuncSetAttribute(k_tile_sort<MAX_ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tile_sort<MAX_ITEMS><<<nvt, TS_THREADS, smem, st>>>(counts, offsets, bucket, point_list, ranges);
+    GS_CUDA_OK(cudaGetLastError());
+    return GS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fallback path (device-wide radix sorts)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __host__ __forceinline__ uint32_t rect_tiles(ushort4 r) {
+    return (r.z > r.x && r.w > r.y) ? (uint32_t)(r.z - r.x) * (uint32_t)(r.w - r.y) : 0u;
+}
+
+__global__ void k_depth_keys(size_t n, const float4 *__restrict__ rec2, const ushort4 *__restrict__ rects,
+                             uint64_t *__restrict__ keys) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    // Gaussians without tiles sort to the end (their records were never written)
+    const uint32_t d = rect_tiles(rects[g]) ? __float_as_uint(rec2[g].y) : 0xffffffffu;
+    keys[g] = ((uint64_t)d << 32) | (uint64_t)g;
+}
+
+struct TilesInOrder {  // tile count gathered through the depth order (input functor of the scan)
+    const ushort4 *rects;
+    __host__ __device__ __forceinline__ uint32_t operator()(const uint64_t &key) const {
+        return rect_tiles(rects[(uint32_t)key]);
+    }
+};
+
+__global__ void k_emit_ordered(const DevCfg c, const uint64_t *__restrict__ order, const ushort4 *__restrict__ rects,
+                               const uint32_t *__restrict__ offsets, uint32_t *__restrict__ keys,
+                               uint32_t *__restrict__ vals) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= (size_t)c.V * c.P) return;
+    const uint32_t g = (uint32_t)order[j];
+    const ushort4 r = rects[g];
+    if (rect_tiles(r) == 0) return;
+    uint32_t off = j == 0 ? 0u : offsets[j - 1];
+    const uint32_t v = g / (uint32_t)c.P;
+    const uint32_t i = g - v * (uint32_t)c.P;
+    const uint32_t tbase = v * (uint32_t)c.ntiles;
+    for (int y = r.y; y < r.w; y++)
+        for (int x = r.x; x < r.z; x++) {
+            keys[off] = tbase + (uint32_t)(y * c.gx + x);
             vals[off] = i;
             off++;
         }
 }
 
-__global__ void k_ranges(int64_t D, const uint64_t *__restrict__ keys, uint2 *__restrict__ ranges) {
+__global__ void k_ranges(int64_t D, const uint32_t *__restrict__ keys, uint2 *__restrict__ ranges) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= D) return;
-    const uint32_t t = (uint32_t)(keys[idx] >> 32);
-    if (idx == 0 || t != (uint32_t)(keys[idx - 1] >> 32)) ranges[t].x = (uint32_t)idx;
-    if (idx == D - 1 || t != (uint32_t)(keys[idx + 1] >> 32)) ranges[t].y = (uint32_t)(idx + 1);
+    const uint32_t t = keys[idx];
+    if (idx == 0 || t != keys[idx - 1]) ranges[t].x = (uint32_t)idx;
+    if (idx == D - 1 || t != keys[idx + 1]) ranges[t].y = (uint32_t)(idx + 1);
 }
 
-inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-
-int sort_bits(const DevCfg &c) {
-    int tb = 0;
+int tile_bits(const DevCfg &c) {
+    int tb = 1;
     while ((1ll << tb) < (long long)c.V * c.ntiles) tb++;
-    return 32 + tb;
+    return tb;
+}
+
+size_t cub_temp_bytes(const DevCfg &c, int64_t n, int64_t D) {
+    size_t t1 = 0, t2 = 0, t3 = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, t1, (const uint64_t *)nullptr, (uint64_t *)nullptr, (int)n, 32, 64);
+    cub::TransformInputIterator<uint32_t, TilesInOrder, const uint64_t *> it(nullptr, TilesInOrder{nullptr});
+    cub::DeviceScan::InclusiveSum(nullptr, t2, it, (uint32_t *)nullptr, (int)n);
+    cub::DeviceRadixSort::SortPairs(nullptr, t3, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)D, 0, tile_bits(c));
+    size_t t = t1 > t2 ? t1 : t2;
+    return align256(t > t3 ? t : t3);
 }
 
 }  // namespace
 
-size_t bin_scan_temp_bytes(int64_t n) {
-    size_t bytes = 0;
-    cub::DeviceScan::InclusiveSum(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n);
-    return align256(bytes);
-}
+size_t bin_counter_bytes(const DevCfg &c) { return (size_t)c.V * c.ntiles * BIN_SUB * BIN_PAD * sizeof(uint32_t); }
 
-int bin_scan(const DevCfg &c, const uint32_t *tiles_touched, uint32_t *offsets, void *temp, size_t temp_bytes,
-             cudaStream_t st) {
-    const int64_t n = (int64_t)c.V * c.P;
-    if (n == 0) return GS_OK;
-    GS_CUDA_OK(cub::DeviceScan::InclusiveSum(temp, temp_bytes, tiles_touched, offsets, (int)n, st));
+int bin_tile_scan(const DevCfg &c, const uint32_t *counters, uint32_t *offsets, uint32_t *tile_start, uint32_t *tile_n,
+                  uint32_t *info, cudaStream_t st) {
+    k_tile_scan<<<1, SCAN_THREADS, 0, st>>>(c.V * c.ntiles, counters, offsets, tile_start, tile_n, info);
+    GS_CUDA_OK(cudaGetLastError());
     return GS_OK;
 }
 
-// scratch = keys_in[D] | keys_out[D] | vals_in[D] | cub temp
-size_t bin_scratch_bytes(const DevCfg &c, int64_t D) {
-    size_t temp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, temp, (const uint64_t *)nullptr, (uint64_t *)nullptr,
-                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)D, 0, sort_bits(c));
-    return 2 * align256((size_t)D * 8) + align256((size_t)D * 4) + align256(temp);
+bool bin_fits_fast_path(uint32_t max_count) { return max_count <= (uint32_t)BIN_SMEM_CAP; }
+
+size_t bin_scratch_bytes(const DevCfg &c, int64_t D, bool fast) {
+    const size_t n = (size_t)c.V * c.P;
+    if (fast) return align256((size_t)(D > 0 ? D : 1) * 8);
+    // depth_keys[n] | order[n] | offsets[n] | keys_in[D] | keys_out[D] | vals_in[D] | cub temp
+    return 2 * align256(n * 8) + align256(n * 4) + 3 * align256((size_t)D * 4) + cub_temp_bytes(c, (int64_t)n, D);
 }
 
-int bin_sort(const DevCfg &c, int64_t D, const float4 *rec2, const uint32_t *tiles_touched, const ushort4 *rects,
-             const uint32_t *offsets, void *scratch, size_t scratch_bytes, uint32_t *point_list, uint2 *ranges,
-             cudaStream_t st) {
+int bin_sort_fast(const DevCfg &c, int64_t D, uint32_t max_count, const float4 *rec2, const ushort4 *rects,
+                  const uint32_t *offsets, const uint32_t *tile_start, const uint32_t *tile_n, uint32_t *cursor,
+                  void *scratch, uint32_t *point_list, uint2 *ranges, cudaStream_t st) {
+    const int nvt = c.V * c.ntiles;
+    uint64_t *bucket = static_cast<uint64_t *>(scratch);
+    if (D > 0) {
+        GS_CUDA_OK(cudaMemsetAsync(cursor, 0, bin_counter_bytes(c), st));
+        const size_t n = (size_t)c.V * c.P;
+        k_emit_buckets<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c, rec2, rects, offsets, cursor, bucket);
+        GS_CUDA_OK(cudaGetLastError());
+    }
+    if (max_count <= TS_THREADS * 2) return launch_tile_sort<2>(nvt, tile_n, tile_start, bucket, point_list, ranges, st);
+    if (max_count <= TS_THREADS * 8) return launch_tile_sort<8>(nvt, tile_n, tile_start, bucket, point_list, ranges, st);
+    if (max_count <= TS_THREADS * 16) return launch_tile_sort<16>(nvt, tile_n, tile_start, bucket, point_list, ranges, st);
+    return launch_tile_sort<BIN_SMEM_CAP / TS_THREADS>(nvt, tile_n, tile_start, bucket, point_list, ranges, st);
+}
+
+int bin_sort_fallback(const DevCfg &c, int64_t D, const float4 *rec2, const ushort4 *rects, void *scratch,
+                      size_t scratch_bytes, uint32_t *point_list, uint2 *ranges, cudaStream_t st) {
     GS_CUDA_OK(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)c.V * c.ntiles, st));
     if (D == 0) return GS_OK;
-    unsigned char *p = static_cast<unsigned char *>(scratch);
-    uint64_t *keys_in = reinterpret_cast<uint64_t *>(p);
-    p += align256((size_t)D * 8);
-    uint64_t *keys_out = reinterpret_cast<uint64_t *>(p);
-    p += align256((size_t)D * 8);
-    uint32_t *vals_in = reinterpret_cast<uint32_t *>(p);
-    p += align256((size_t)D * 4);
-    void *temp = p;
-    size_t temp_bytes = scratch_bytes - (size_t)(p - static_cast<unsigned char *>(scratch));
-
     const size_t n = (size_t)c.V * c.P;
-    k_duplicate<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c, rec2, tiles_touched, rects, offsets, keys_in, vals_in);
+    unsigned char *p = static_cast<unsigned char *>(scratch);
+    auto take = [&](size_t bytes) {
+        unsigned char *q = p;
+        p += align256(bytes);
+        return q;
+    };
+    uint64_t *depth_keys = reinterpret_cast<uint64_t *>(take(n * 8));
+    uint64_t *order = reinterpret_cast<uint64_t *>(take(n * 8));
+    uint32_t *offsets = reinterpret_cast<uint32_t *>(take(n * 4));
+    uint32_t *keys_in = reinterpret_cast<uint32_t *>(take((size_t)D * 4));
+    uint32_t *keys_out = reinterpret_cast<uint32_t *>(take((size_t)D * 4));
+    uint32_t *vals_in = reinterpret_cast<uint32_t *>(take((size_t)D * 4));
+    size_t temp_bytes = scratch_bytes - (size_t)(p - static_cast<unsigned char *>(scratch));
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+
+    k_depth_keys<<<blocks, 256, 0, st>>>(n, rec2, rects, depth_keys);
     GS_CUDA_OK(cudaGetLastError());
-    GS_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, point_list, (int)D, 0,
-                                               sort_bits(c), st));
+    GS_CUDA_OK(cub::DeviceRadixSort::SortKeys(p, temp_bytes, depth_keys, order, (int)n, 32, 64, st));
+    cub::TransformInputIterator<uint32_t, TilesInOrder, const uint64_t *> it(order, TilesInOrder{rects});
+    GS_CUDA_OK(cub::DeviceScan::InclusiveSum(p, temp_bytes, it, offsets, (int)n, st));
+    k_emit_ordered<<<blocks, 256, 0, st>>>(c, order, rects, offsets, keys_in, vals_in);
+    GS_CUDA_OK(cudaGetLastError());
+    GS_CUDA_OK(cub::DeviceRadixSort::SortPairs(p, temp_bytes, keys_in, keys_out, vals_in, point_list, (int)D, 0,
+                                               tile_bits(c), st));
     k_ranges<<<(unsigned)((D + 255) / 256), 256, 0, st>>>(D, keys_out, ranges);
     GS_CUDA_OK(cudaGetLastError());
     return GS_OK;

@@ -47,10 +47,10 @@ struct GrowBuf {
 };
 
 struct GsContext {
-    GrowBuf per_gaussian;  // tiles_touched | offsets | rects | scan temp ; backward: accumulators
-    GrowBuf sort;          // keys_in | keys_out | vals_in | cub temp
+    GrowBuf per_gaussian;  // rects | tile counts / offsets / cursors ; backward: accumulators
+    GrowBuf sort;          // buckets (fast path) or radix-sort buffers (fallback)
     GrowBuf host_stage;    // device mirror of host buffers (gs_render_host)
-    uint32_t *h_word = nullptr;  // pinned
+    uint32_t *h_word = nullptr;  // pinned: [0] = tile instances, [1] = longest tile list
     GsStats stats{};
     bool profiling = false;
     cudaEvent_t ev[GS_NUM_STAGES + 1][2]{};
@@ -155,6 +155,14 @@ extern "C" int gs_context_create(GsContext **out) {
     if (cudaGetDevice(&dev) != cudaSuccess) return gs_set_error(GS_ERR_NO_DEVICE, "no CUDA device");
     GsContext *ctx = new (std::nothrow) GsContext();
     if (!ctx) return gs_set_error(GS_ERR_OOM, "host allocation failed");
+    // Saved state lives in the device's default stream-ordered pool.  Its default release threshold (0) hands
+    // every freed block back to the OS at the next synchronisation -- and each forward synchronises once -- so
+    // keep freed blocks cached in the pool instead.
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&ctx->h_word), 64);
     if (e != cudaSuccess) {
         delete ctx;
@@ -233,16 +241,26 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     for (bool &v : ctx->ev_valid) v = false;
     ctx->stats.kernel_launches = 0;
 
-    // ---- per-Gaussian scratch: tiles_touched | offsets | rects | scan temp ----
-    const size_t scan_temp = bin_scan_temp_bytes((int64_t)n);
-    const size_t pg_bytes = 2 * align256(n * 4) + align256(n * 8) + scan_temp;
+    // ---- per-call scratch: rects[n] | counters | cursors | sub-bucket offsets | tile_start | tile_n | info ----
+    const size_t nvt = (size_t)c.V * c.ntiles;
+    const size_t ctr_bytes = align256(bin_counter_bytes(c));
+    const size_t pg_bytes = align256(n * 8) + 2 * ctr_bytes + align256(nvt * BIN_SUB * 4) + 2 * align256(nvt * 4) + 256;
     rc = ctx->per_gaussian.reserve(pg_bytes, 1.0);
     if (rc != GS_OK) return rc;
     unsigned char *pg = static_cast<unsigned char *>(ctx->per_gaussian.p);
-    uint32_t *tiles_touched = reinterpret_cast<uint32_t *>(pg);
-    uint32_t *offsets = reinterpret_cast<uint32_t *>(pg + align256(n * 4));
-    ushort4 *rects = reinterpret_cast<ushort4 *>(pg + 2 * align256(n * 4));
-    void *scan_tmp = pg + 2 * align256(n * 4) + align256(n * 8);
+    ushort4 *rects = reinterpret_cast<ushort4 *>(pg);
+    pg += align256(n * 8);
+    uint32_t *tile_counts = reinterpret_cast<uint32_t *>(pg);
+    pg += ctr_bytes;
+    uint32_t *cursor = reinterpret_cast<uint32_t *>(pg);
+    pg += ctr_bytes;
+    uint32_t *sub_offsets = reinterpret_cast<uint32_t *>(pg);
+    pg += align256(nvt * BIN_SUB * 4);
+    uint32_t *tile_start = reinterpret_cast<uint32_t *>(pg);
+    pg += align256(nvt * 4);
+    uint32_t *tile_n = reinterpret_cast<uint32_t *>(pg);
+    pg += align256(nvt * 4);
+    uint32_t *info = reinterpret_cast<uint32_t *>(pg);
 
     // ---- saved state: geometry / image planes now, the tile-instance list once its length is known ----
     GsSaved *s = new (std::nothrow) GsSaved();
@@ -267,7 +285,9 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
 
     {
         StageTimer t(ctx, GS_STAGE_PREPROCESS, st);
-        rc = launch_preprocess(c, di, s->rec0, s->rec1, s->rec2, s->meta, out->radii, tiles_touched, rects, st);
+        cudaError_t e = cudaMemsetAsync(tile_counts, 0, bin_counter_bytes(c), st);
+        if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "cudaMemsetAsync(tile_counts)", __FILE__, __LINE__));
+        rc = launch_preprocess(c, di, s->rec0, s->rec1, s->rec2, s->meta, out->radii, rects, tile_counts, st);
         if (rc != GS_OK) return fail(rc);
         ctx->stats.kernel_launches += (c.P > 0);
     }
@@ -275,29 +295,33 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     int64_t D = 0;
     {
         StageTimer t(ctx, GS_STAGE_BIN, st);
-        if (n > 0) {
-            rc = bin_scan(c, tiles_touched, offsets, scan_tmp, scan_temp, st);
-            if (rc != GS_OK) return fail(rc);
-            cudaError_t e = cudaMemcpyAsync(ctx->h_word, offsets + (n - 1), 4, cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the one host sync of the forward
-            if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "read back num_rendered", __FILE__, __LINE__));
-            D = (int64_t)*ctx->h_word;
-        }
+        rc = bin_tile_scan(c, tile_counts, sub_offsets, tile_start, tile_n, info, st);
+        if (rc != GS_OK) return fail(rc);
+        cudaError_t e = cudaMemcpyAsync(ctx->h_word, info, 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the one host sync of the forward
+        if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "read back num_rendered", __FILE__, __LINE__));
+        D = (int64_t)ctx->h_word[0];
+        const uint32_t max_count = ctx->h_word[1];
         if (D > 0x7fffffffll) return fail(gs_set_error(GS_ERR_OVERFLOW, "more than 2^31-1 tile instances"));
         // the list lives in its own stream-ordered allocation (sized exactly)
-        cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&s->point_list), (size_t)(D > 0 ? D : 1) * 4, st);
+        e = cudaMallocAsync(reinterpret_cast<void **>(&s->point_list), (size_t)(D > 0 ? D : 1) * 4, st);
         if (e != cudaSuccess) {
             s->point_list = nullptr;
             return fail(gs_set_cuda_error(e, "cudaMallocAsync(point_list)", __FILE__, __LINE__));
         }
         s->D = D;
-        const size_t sort_bytes = bin_scratch_bytes(c, D);
-        rc = ctx->sort.reserve(sort_bytes, 1.25);
-        if (rc == GS_OK)
-            rc = bin_sort(c, D, s->rec2, tiles_touched, rects, offsets, ctx->sort.p, ctx->sort.bytes, s->point_list,
-                          s->ranges, st);
+        const bool fast = bin_fits_fast_path(max_count) && !(cfg->tuning & GS_TUNE_FORCE_RADIX_BINNING);
+        rc = ctx->sort.reserve(bin_scratch_bytes(c, D, fast), 1.25);
+        if (rc == GS_OK) {
+            if (fast)
+                rc = bin_sort_fast(c, D, max_count, s->rec2, rects, sub_offsets, tile_start, tile_n, cursor, ctx->sort.p,
+                                   s->point_list, s->ranges, st);
+            else
+                rc = bin_sort_fallback(c, D, s->rec2, rects, ctx->sort.p, ctx->sort.bytes, s->point_list, s->ranges, st);
+        }
         if (rc != GS_OK) return fail(rc);
-        ctx->stats.kernel_launches += D > 0 ? 2 : 0;  // k_duplicate, k_ranges (CUB's scan/sort launches not counted)
+        ctx->stats.kernel_launches += 1 + (D > 0 ? 1 : 0) + 1;  // scan, emit, tile sort (fallback: 3 + CUB's)
+        ctx->stats.max_tile_list = (int32_t)max_count;
     }
 
     {

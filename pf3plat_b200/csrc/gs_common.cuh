@@ -57,16 +57,23 @@ int gs_set_error(int code, const char *msg);
 
 // ---- kernel launchers (one translation unit per stage) ----
 int launch_preprocess(const DevCfg &c, const DevInputs &in, float4 *rec0, float4 *rec1, float4 *rec2, uint8_t *meta,
-                      int32_t *radii, uint32_t *tiles_touched, ushort4 *rects, cudaStream_t st);
+                      int32_t *radii, ushort4 *rects, uint32_t *tile_counters /* padded sub-counters, zeroed */, cudaStream_t st);
 int launch_mark_visible(const DevCfg &c, const float *means3D, uint8_t *present, cudaStream_t st);
 
-size_t bin_scratch_bytes(const DevCfg &c, int64_t D);
-int bin_scan(const DevCfg &c, const uint32_t *tiles_touched, uint32_t *offsets, void *temp, size_t temp_bytes,
-             cudaStream_t st);
-size_t bin_scan_temp_bytes(int64_t n);
-int bin_sort(const DevCfg &c, int64_t D, const float4 *rec2, const uint32_t *tiles_touched, const ushort4 *rects,
-             const uint32_t *offsets, void *scratch, size_t scratch_bytes, uint32_t *point_list, uint2 *ranges,
-             cudaStream_t st);
+// binning (gs_binning.cu)
+#define BIN_SMEM_CAP 8192  // longest tile list the shared-memory merge sort takes (256 threads x 32 keys)
+#define BIN_SUB 8          // sub-counters per (view, tile), selected by Gaussian index & (BIN_SUB-1)
+#define BIN_PAD 8          // uint32 stride between counters: one counter per 32-byte L2 sector
+size_t bin_counter_bytes(const DevCfg &c);
+int bin_tile_scan(const DevCfg &c, const uint32_t *counters, uint32_t *offsets, uint32_t *tile_start, uint32_t *tile_n,
+                  uint32_t *info, cudaStream_t st);
+bool bin_fits_fast_path(uint32_t max_count);
+size_t bin_scratch_bytes(const DevCfg &c, int64_t D, bool fast);
+int bin_sort_fast(const DevCfg &c, int64_t D, uint32_t max_count, const float4 *rec2, const ushort4 *rects,
+                  const uint32_t *offsets, const uint32_t *tile_start, const uint32_t *tile_n, uint32_t *cursor,
+                  void *scratch, uint32_t *point_list, uint2 *ranges, cudaStream_t st);
+int bin_sort_fallback(const DevCfg &c, int64_t D, const float4 *rec2, const ushort4 *rects, void *scratch,
+                      size_t scratch_bytes, uint32_t *point_list, uint2 *ranges, cudaStream_t st);
 
 int launch_composite_fwd(const DevCfg &c, const GsSaved &s, float *color, float *depth, cudaStream_t st);
 int launch_composite_bwd(const DevCfg &c, const GsSaved &s, const float *dL_dcolor, const float *dL_ddepth,

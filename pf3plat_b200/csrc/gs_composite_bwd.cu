@@ -43,18 +43,19 @@ struct PixState {
     uint32_t last;  // number of list entries this pixel walked up to its last contributor
 };
 
+// Returns whether this pixel received the Gaussian (and hence wrote non-trivial partial gradients to g).
 template <bool DEPTH>
-__device__ __forceinline__ void pixel_grad(PixState &ps, bool live, float4 q0, float4 q1, float4 q2, float pxf,
+__device__ __forceinline__ bool pixel_grad(PixState &ps, bool live, float4 q0, float4 q1, float4 q2, float pxf,
                                            float pyf, float half_w, float half_h, float *g /* [GS_ACC_STRIDE] */) {
 #pragma unroll
     for (int k = 0; k < GS_ACC_STRIDE; k++) g[k] = 0.f;
-    if (!live) return;
+    if (!live) return false;
     const float dx = q0.x - pxf, dy = q0.y - pyf;
     const float p2 = gs_power2(q0.z, q0.w, q1.x, dx, dy);
-    if (p2 > 0.0f) return;
+    if (p2 > 0.0f) return false;
     const float G = gs_ex2(p2);
     const float alpha = fminf(GS_ALPHA_MAX, q1.y * G);
-    if (alpha < GS_ALPHA_MIN) return;
+    if (alpha < GS_ALPHA_MIN) return false;
     ps.T = ps.T / (1.0f - alpha);
     const float w = alpha * ps.T;
     const float col[3] = {q1.z, q1.w, q2.x};
@@ -87,6 +88,7 @@ __device__ __forceinline__ void pixel_grad(PixState &ps, bool live, float4 q0, f
     g[6] = -0.5f * gdx * dy * dL_dG;
     g[7] = -0.5f * gdy * dy * dL_dG;
     g[8] = G * dL_dalpha;
+    return true;
 }
 
 template <bool DEPTH>
@@ -171,6 +173,7 @@ k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
             while (mask) {
                 float gv[32];
                 uint32_t gid[CB_GROUP];
+                bool any_got = false;
 #pragma unroll
                 for (int slot = 0; slot < CB_GROUP; slot++) {
                     float *g = gv + slot * GS_ACC_STRIDE;
@@ -179,13 +182,15 @@ k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
                         mask &= ~(1u << b);
                         const uint32_t jj = (uint32_t)chunk + b;
                         gid[slot] = sid[jj];
-                        pixel_grad<DEPTH>(ps, lo + jj < ps.last, s0[jj], s1[jj], s2[jj], pxf, pyf, half_w, half_h, g);
+                        any_got |= pixel_grad<DEPTH>(ps, lo + jj < ps.last, s0[jj], s1[jj], s2[jj], pxf, pyf, half_w,
+                                                     half_h, g);
                     } else {
                         gid[slot] = 0xffffffffu;
 #pragma unroll
                         for (int k = 0; k < GS_ACC_STRIDE; k++) g[k] = 0.f;
                     }
                 }
+                if (!__any_sync(0xffffffffu, any_got)) continue;  // box hits that reached no pixel: nothing to add
                 gv[30] = gv[31] = 0.f;
                 const float total = butterfly_reduce32(gv, lane);
                 const int slot = lane / GS_ACC_STRIDE, comp = lane - slot * GS_ACC_STRIDE;

@@ -143,7 +143,7 @@ template <bool HAS_SH>
 __global__ void __launch_bounds__(PRE_THREADS)
 k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, float4 *__restrict__ rec1,
              float4 *__restrict__ rec2, uint8_t *__restrict__ meta, int32_t *__restrict__ radii,
-             uint32_t *__restrict__ tiles_touched, ushort4 *__restrict__ rects) {
+             ushort4 *__restrict__ rects, uint32_t *__restrict__ tile_counts) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PreSmem *sm = reinterpret_cast<PreSmem *>(smem_raw);
     float *sh_s = reinterpret_cast<float *>(smem_raw + 256);  // PreSmem fits in 256 bytes
@@ -211,8 +211,13 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
             rec2[o] = sp.r2;
         }
         radii[o] = sp.radius;
-        tiles_touched[o] = sp.tiles;
         rects[o] = sp.rect;
+        // count this Gaussian into every (view, tile) list it will join (binning step 1: RED.ADD, no return;
+        // sub-counter i % BIN_SUB, one counter per 32-byte sector -- see gs_binning.cu)
+        for (int ty = sp.rect.y; ty < sp.rect.w; ty++)
+            for (int tx = sp.rect.x; tx < sp.rect.z; tx++)
+                atomicAdd(&tile_counts[(((size_t)v * c.ntiles + ty * c.gx + tx) * BIN_SUB + (i & (BIN_SUB - 1))) * BIN_PAD],
+                          1u);
         meta[o] = (uint8_t)sp.meta;
     }
 }
@@ -233,15 +238,15 @@ __global__ void k_mark_visible(const DevCfg c, const float *__restrict__ means3D
 }  // namespace
 
 int launch_preprocess(const DevCfg &c, const DevInputs &in, float4 *rec0, float4 *rec1, float4 *rec2, uint8_t *meta,
-                      int32_t *radii, uint32_t *tiles_touched, ushort4 *rects, cudaStream_t st) {
+                      int32_t *radii, ushort4 *rects, uint32_t *tile_counts, cudaStream_t st) {
     if (c.P == 0) return GS_OK;
     dim3 grid((c.P + PRE_THREADS - 1) / PRE_THREADS, c.S);
     if (in.shs) {
         size_t smem = 256 + (size_t)PRE_THREADS * c.M * 12;
         GS_CUDA_OK(cudaFuncSetAttribute(k_preprocess<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_preprocess<true><<<grid, PRE_THREADS, smem, st>>>(c, in, rec0, rec1, rec2, meta, radii, tiles_touched, rects);
+        k_preprocess<true><<<grid, PRE_THREADS, smem, st>>>(c, in, rec0, rec1, rec2, meta, radii, rects, tile_counts);
     } else {
-        k_preprocess<false><<<grid, PRE_THREADS, 256, st>>>(c, in, rec0, rec1, rec2, meta, radii, tiles_touched, rects);
+        k_preprocess<false><<<grid, PRE_THREADS, 256, st>>>(c, in, rec0, rec1, rec2, meta, radii, rects, tile_counts);
     }
     GS_CUDA_OK(cudaGetLastError());
     return GS_OK;

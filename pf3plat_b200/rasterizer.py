@@ -119,6 +119,7 @@ class BatchSettings(NamedTuple):
     prefiltered: bool = False
     with_depth: bool = False
     debug: bool = False
+    tuning: int = 0                          # GS_TUNE_* knobs (testing)
 
 
 def _make_config(bs: BatchSettings, S: int, P: int, M: int, keep: list) -> GsConfig:
@@ -131,6 +132,7 @@ def _make_config(bs: BatchSettings, S: int, P: int, M: int, keep: list) -> GsCon
     cfg.flags = (_capi.GS_FLAG_DEPTH if bs.with_depth else 0) | (_capi.GS_FLAG_PREFILTERED if bs.prefiltered else 0)
     cfg.tanfovx, cfg.tanfovy = float(bs.tanfovx), float(bs.tanfovy)
     cfg.scale_modifier = float(bs.scale_modifier)
+    cfg.tuning = int(bs.tuning)
     tensors = {
         "viewmatrix": _f32c(bs.viewmatrix).reshape(V, 16), "projmatrix": _f32c(bs.projmatrix, dev).reshape(V, 16),
         "campos": _f32c(bs.campos, dev).reshape(V, 3), "bg": _f32c(bs.bg, dev).reshape(V, 3),

@@ -197,3 +197,37 @@ def test_determinism_and_linearity_at_full_size():
     (gb,) = torch.autograd.grad((c1 * (2 * g)).sum(), leaves["means"])
     assert relerr(gb, (2 * ga).cpu().numpy()) < 1e-5     # float atomics reorder sums: not bit-exact
     assert torch.isfinite(ga).all()
+
+
+def _render_with_tuning(sc, dev, tuning):
+    from pf3plat_b200.cameras import make_view_batch
+    from pf3plat_b200.rasterizer import BatchSettings, last_stats, rasterize_batch
+    d = sc.to(dev)
+    vb = make_view_batch(d.extrinsics, d.intrinsics, d.near, d.far)
+    h, w = sc.image_shape
+    bs = BatchSettings(image_height=h, image_width=w, viewmatrix=vb.viewmatrix, projmatrix=vb.projmatrix,
+                       campos=vb.campos, bg=d.background, sh_degree=4, tanfov=vb.tanfov, view_scale=vb.scale,
+                       tuning=tuning)
+    c = d.covariances
+    cov6 = torch.stack([c[:, 0, 0], c[:, 0, 1], c[:, 0, 2], c[:, 1, 1], c[:, 1, 2], c[:, 2, 2]], -1)
+    color, radii = rasterize_batch(bs, d.means[None], d.opacities[None], shs=d.harmonics.permute(0, 2, 1)[None],
+                                   cov3D_precomp=cov6[None])
+    return color, last_stats(dev)
+
+
+def test_binning_paths_agree_bit_for_bit():
+    """Shared-memory bucket sort (fast path) vs device-wide radix sort (fallback) give the same lists, hence the
+    same pixels; and a scene whose densest tile exceeds the shared-memory capacity takes the fallback by itself."""
+    from pf3plat_b200._capi import GS_TUNE_FORCE_RADIX_BINNING
+    dev = _dev()
+    sc = make_scene(30000, 2, 64, 96, seed=7)
+    fast, st_fast = _render_with_tuning(sc, dev, 0)
+    slow, st_slow = _render_with_tuning(sc, dev, GS_TUNE_FORCE_RADIX_BINNING)
+    assert st_fast["num_rendered"] == st_slow["num_rendered"] and st_fast["max_tile_list"] <= 8192
+    assert torch.equal(fast, slow)
+    # 40k Gaussians squeezed into the centre of a 32x32 image: > 8192 entries in one tile
+    dense = make_scene(40000, 1, 32, 32, seed=8)
+    dense.means[:, :2] *= 0.05
+    color, st = _render_with_tuning(dense, dev, 0)
+    assert st["max_tile_list"] > 8192
+    check_image(color[0], oracle_view(dense, 0), max_fragile_frac=0.2)
