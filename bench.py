@@ -136,8 +136,13 @@ def main():
     from pf3plat_b200 import _capi, rasterizer
     from pf3plat_b200.cameras import make_view_batch
     from pf3plat_b200.rasterizer import BatchSettings, rasterize_batch
+    from pf3plat_b200.sharding import gather_metric, shard_views
     from pf3plat_b200.synthetic import make_scene, make_target
 
+    # on the GPU box NCCL prints a "NCCL version ..." banner on stdout (NCCL_DEBUG=VERSION via env or nccl.conf),
+    # next to the one JSON line this script owes its caller; an explicit NCCL_DEBUG=INFO etc. is left alone
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -148,7 +153,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- synthetic workload: this rank's 8 views of the shared cloud ----
-    sc = make_scene(P_GAUSS, VIEWS, HW, HW, seed=0, first_view=rank * VIEWS, total_views=world * VIEWS)
+    my_views = shard_views(world * VIEWS, rank, world)   # weak scaling: 8 views per rank
+    sc = make_scene(P_GAUSS, len(my_views), HW, HW, seed=0, first_view=my_views[0], total_views=world * VIEWS)
     vb = make_view_batch(sc.extrinsics, sc.intrinsics, sc.near, sc.far, scale_invariant=True)
     host = {
         "means3D": sc.means.reshape(1, P_GAUSS, 3), "opacities": sc.opacities.reshape(1, P_GAUSS),
@@ -253,11 +259,7 @@ def main():
 
     # PSNR of each view against the target, gathered over ranks (the only collective of the job)
     mse = ((color - target) ** 2).mean(dim=(1, 2, 3))
-    psnr = -10 * torch.log10(mse)
-    if world > 1:
-        allp = [torch.empty_like(psnr) for _ in range(world)]
-        dist.all_gather(allp, psnr)
-        psnr = torch.cat(allp)
+    psnr = gather_metric(-10 * torch.log10(mse))
 
     if rank == 0:
         hbm, hbm_src = peaks()
@@ -329,7 +331,8 @@ def main():
             "clocks": clocks,
             "psnr_vs_target_mean": float(psnr.mean().item()),
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -207,6 +207,12 @@ __device__ __forceinline__ float gs_ex2(float x) {
     return y;
 }
 
+__device__ __forceinline__ float gs_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 #define GS_SH_C0 0.28209479177387814f
 #define GS_SH_C1 0.4886025119029199f
 #define GS_SH_C2_0 1.0925484305920792f

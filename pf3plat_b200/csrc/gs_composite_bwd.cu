@@ -56,7 +56,10 @@ __device__ __forceinline__ bool pixel_grad(PixState &ps, bool live, float4 q0, f
     const float G = gs_ex2(p2);
     const float alpha = fminf(GS_ALPHA_MAX, q1.y * G);
     if (alpha < GS_ALPHA_MIN) return false;
-    ps.T = ps.T / (1.0f - alpha);
+    // one approximate reciprocal (MUFU.RCP, <= 1 ulp) serves both divisions by (1 - alpha); the IEEE divisions
+    // upstream uses cost ~10 instructions each and the 1e-3 gradient tolerance does not need them
+    const float inv_1ma = gs_rcp(1.0f - alpha);
+    ps.T = ps.T * inv_1ma;
     const float w = alpha * ps.T;
     const float col[3] = {q1.z, q1.w, q2.x};
     float dL_dalpha = 0.f;
@@ -75,7 +78,7 @@ __device__ __forceinline__ bool pixel_grad(PixState &ps, bool live, float4 q0, f
     }
     dL_dalpha *= ps.T;
     ps.last_alpha = alpha;
-    dL_dalpha += (-ps.T_final / (1.0f - alpha)) * ps.bg_dot;
+    dL_dalpha -= ps.T_final * inv_1ma * ps.bg_dot;
     const float dL_dG = q1.y * dL_dalpha;  // straight through the 0.99 clamp
     // true conic from the pre-scaled record: A = hA * (-2/log2e), B = nB * (-1/log2e)
     const float A = q0.z * (-2.0f / GS_LOG2E), B = q0.w * (-1.0f / GS_LOG2E), Cc = q1.x * (-2.0f / GS_LOG2E);

@@ -1,0 +1,66 @@
+"""Host logic of the multi-GPU path, on CPU with the gloo backend (world_size 2): the view sharding used by
+bench.py (rank r renders views [8r, 8r+8) of the shared cloud, no data-path collective) and the only collective
+of the job, an all-gather of per-view PSNR.  The CUDA op itself is not called here (no GPU)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pf3plat_b200.cameras import make_view_batch
+from pf3plat_b200.sharding import gather_metric, shard_views
+from pf3plat_b200.synthetic import make_scene
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        views = list(shard_views(8, rank, world))
+        psnr_local = torch.tensor([float(v) for v in views])
+        allp = gather_metric(psnr_local)
+        sc = make_scene(100, len(views), 32, 32, first_view=views[0], total_views=8)
+        out.put((rank, views, allp.tolist(), sc.extrinsics[:, :2, 3].tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_view_sharding_and_psnr_gather_world2():
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, v0, g0, t0), (r1, v1, g1, t1) = res
+    assert v0 == [0, 1, 2, 3] and v1 == [4, 5, 6, 7]               # contiguous, disjoint, complete
+    assert g0 == g1 == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0]    # every rank sees every view's metric, in view order
+    full = make_scene(100, 8, 32, 32).extrinsics[:, :2, 3].tolist()
+    assert t0 + t1 == full                                          # shards reproduce the unsharded camera path
+
+
+def test_shard_views_covers_ragged_splits():
+    for n, world in [(8, 1), (8, 3), (5, 4), (32, 8), (3, 8)]:
+        got = [v for r in range(world) for v in shard_views(n, r, world)]
+        assert got == list(range(n))
+        sizes = [len(shard_views(n, r, world)) for r in range(world)]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_view_batch_has_no_host_sync_inputs():
+    sc = make_scene(10, 3, 16, 16)
+    vb = make_view_batch(sc.extrinsics, sc.intrinsics, sc.near, sc.far)
+    assert vb.viewmatrix.shape == (3, 4, 4) and vb.tanfov.shape == (3, 2)
+    assert torch.allclose(vb.tanfov, torch.full((3, 2), 0.5 / 0.86), atol=1e-5)
