@@ -62,3 +62,26 @@ def render_like_reference(extrinsics, intrinsics, near, far, image_shape, backgr
     if return_means2d:
         extra.append(all_m2d)
     return (out, *extra) if extra else out
+
+
+def render_depth_like_reference(extrinsics, intrinsics, near, far, image_shape, gaussian_means, gaussian_covariances,
+                                gaussian_opacities, scale_invariant=True, mode="depth"):
+    """Restates render_depth_cuda (/root/reference/src/model/decoder/cuda_splatting.py:226-269): camera-space z (or
+    a function of it) rendered as a 3-channel colour with bg = 0, then averaged over the channels."""
+    hom = torch.cat([gaussian_means, torch.ones_like(gaussian_means[..., :1])], dim=-1)
+    cam = torch.einsum("bij,bgj->bgi", extrinsics.inverse(), hom)
+    fake = cam[..., 2]
+    if mode == "disparity":
+        fake = 1 / fake
+    elif mode == "relative_disparity":
+        eps = 1e-10
+        dn, df, d = 1 / (near[:, None] + eps), 1 / (far[:, None] + eps), 1 / (fake + eps)
+        fake = 1 - (d - df) / (dn - df + eps)
+    elif mode == "log":
+        fake = fake.minimum(near[:, None]).maximum(far[:, None]).log()
+    b = fake.shape[0]
+    result = render_like_reference(extrinsics, intrinsics, near, far, image_shape,
+                                   torch.zeros((b, 3), dtype=fake.dtype, device=fake.device), gaussian_means,
+                                   gaussian_covariances, fake[..., None, None].expand(-1, -1, 3, 1), gaussian_opacities,
+                                   scale_invariant=scale_invariant, use_sh=False)
+    return result.mean(dim=1)

@@ -1,0 +1,97 @@
+"""GPU tests of the decoder-facing surface: the reference's call pattern (tests/ref_callsite.py restates
+cuda_splatting.py line by line) against the batched entry that replaces DecoderSplattingCUDA.forward
+(/root/reference/src/model/decoder/decoder_splatting_cuda.py:35-91)."""
+import pytest
+import torch
+
+from pf3plat_b200.synthetic import make_scene, make_target
+from tests.ref_callsite import render_depth_like_reference, render_like_reference
+
+pytestmark = pytest.mark.gpu
+
+
+def _scenes(dev, b=2, v=3, P=3000, hw=(48, 64), near=1.0):
+    scs = [make_scene(P, v, hw[0], hw[1], seed=20 + k).to(dev) for k in range(b)]
+    st = lambda name: torch.stack([getattr(s, name) for s in scs])
+    ext, intr = st("extrinsics"), st("intrinsics")
+    nr = torch.full((b, v), near, device=dev)
+    fr = torch.full((b, v), 100.0 * near, device=dev)
+    return scs, st("means"), st("covariances"), st("harmonics"), st("opacities"), ext, intr, nr, fr
+
+
+@pytest.mark.parametrize("near", [1.0, 0.5])
+def test_decoder_forward_matches_the_reference_call_pattern(near):
+    from pf3plat_b200.render import decoder_forward
+    dev = torch.device("cuda:0")
+    b, v, hw = 2, 3, (48, 64)
+    scs, means, cov, sh, opac, ext, intr, nr, fr = _scenes(dev, b, v, hw=hw, near=near)
+    bg = torch.tensor([0.1, 0.2, 0.3], device=dev)
+    color, depth = decoder_forward(means, cov, sh, opac, ext, intr, nr, fr, hw, bg, depth_mode="depth")
+    assert color.shape == (b, v, 3, *hw) and depth.shape == (b, v, *hw)
+    flat = lambda t: t.reshape(b * v, *t.shape[2:])
+    rep = lambda t: t.repeat_interleave(v, dim=0)             # what the reference's einops.repeat does
+    ref_c = render_like_reference(flat(ext), flat(intr), flat(nr), flat(fr), hw, bg[None].expand(b * v, 3),
+                                  rep(means), rep(cov), rep(sh), rep(opac))
+    ref_d = render_depth_like_reference(flat(ext), flat(intr), flat(nr), flat(fr), hw, rep(means), rep(cov), rep(opac))
+    # same kernels, same per-view arithmetic: the only difference is where the 1/near rescale is applied
+    assert (color.reshape(b * v, 3, *hw) - ref_c).abs().max() <= 1e-4
+    assert (depth.reshape(b * v, *hw) - ref_d).abs().max() <= 2e-3 * float(ref_d.abs().max())
+
+
+@pytest.mark.parametrize("mode", ["disparity", "relative_disparity", "log"])
+def test_other_depth_modes(mode):
+    from pf3plat_b200.render import render_depth
+    dev = torch.device("cuda:0")
+    b, v, hw = 1, 2, (32, 48)
+    scs, means, cov, sh, opac, ext, intr, nr, fr = _scenes(dev, b, v, P=1500, hw=hw)
+    got = render_depth(means, cov, opac, ext, intr, nr, fr, hw, mode=mode)
+    flat = lambda t: t.reshape(b * v, *t.shape[2:])
+    rep = lambda t: t.repeat_interleave(v, dim=0)
+    ref = render_depth_like_reference(flat(ext), flat(intr), flat(nr), flat(fr), hw, rep(means), rep(cov), rep(opac),
+                                      mode=mode)
+    assert (got.reshape(b * v, *hw) - ref).abs().max() <= 1e-4 * max(1.0, float(ref.abs().max()))
+
+
+def test_gradients_flow_to_the_encoder_side_tensors():
+    from pf3plat_b200.render import decoder_forward
+    dev = torch.device("cuda:0")
+    b, v, hw = 2, 2, (32, 32)
+    scs, means, cov, sh, opac, ext, intr, nr, fr = _scenes(dev, b, v, P=1000, hw=hw)
+    leaves = [t.clone().requires_grad_(True) for t in (means, cov, sh, opac)]
+    color, depth = decoder_forward(*leaves, ext, intr, nr, fr, hw, torch.zeros(3, device=dev), depth_mode="depth")
+    target = make_target(b * v, *hw).to(dev).reshape(b, v, 3, *hw)
+    (((color - target) ** 2).mean() + 1e-3 * depth.mean()).backward()
+    # reference pattern with autograd through the per-view loop and the v-fold repeat
+    leaves_r = [t.clone().requires_grad_(True) for t in (means, cov, sh, opac)]
+    flat = lambda t: t.reshape(b * v, *t.shape[2:])
+    rep = lambda t: t.repeat_interleave(v, dim=0)
+    rc = render_like_reference(flat(ext), flat(intr), flat(nr), flat(fr), hw, torch.zeros(b * v, 3, device=dev),
+                               *[rep(t) for t in leaves_r])
+    rd = render_depth_like_reference(flat(ext), flat(intr), flat(nr), flat(fr), hw, rep(leaves_r[0]), rep(leaves_r[1]),
+                                     rep(leaves_r[3]))
+    (((rc.reshape(b, v, 3, *hw) - target) ** 2).mean() + 1e-3 * rd.mean()).backward()
+    for a, r in zip(leaves, leaves_r):
+        assert a.grad is not None and torch.isfinite(a.grad).all()
+        err = (a.grad - r.grad).abs().max() / r.grad.abs().max()
+        assert err <= 1e-3, float(err)
+
+
+def test_orthographic_style_settings_with_tensor_tanfov():
+    """render_cuda_orthographic passes tanfovx/tanfovy as 0-dim CUDA tensors (cuda_splatting.py:195-196)."""
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    dev = torch.device("cuda:0")
+    sc = make_scene(500, 1, 32, 32, seed=5).to(dev)
+    from pf3plat_b200.cameras import make_view_batch
+    vb = make_view_batch(sc.extrinsics, sc.intrinsics, sc.near, sc.far)
+    common = dict(image_height=32, image_width=32, bg=sc.background[0], scale_modifier=1.0,
+                  viewmatrix=vb.viewmatrix[0], projmatrix=vb.projmatrix[0], sh_degree=4, campos=vb.campos[0],
+                  prefiltered=False, debug=False)
+    row, col = torch.triu_indices(3, 3)
+    args = dict(means3D=sc.means, means2D=torch.zeros_like(sc.means), shs=sc.harmonics.permute(0, 2, 1).contiguous(),
+                opacities=sc.opacities[:, None], cov3D_precomp=sc.covariances[:, row, col])
+    a, _ = GaussianRasterizer(GaussianRasterizationSettings(tanfovx=vb.tanfov[0, 0], tanfovy=vb.tanfov[0, 1], **common))(**args)
+    b_, _ = GaussianRasterizer(GaussianRasterizationSettings(tanfovx=float(vb.tanfov[0, 0]), tanfovy=float(vb.tanfov[0, 1]),
+                                                            **common))(**args)
+    assert torch.equal(a, b_)
+    vis = GaussianRasterizer(GaussianRasterizationSettings(tanfovx=0.58, tanfovy=0.58, **common)).markVisible(sc.means)
+    assert vis.dtype == torch.bool and vis.all()      # every synthetic Gaussian sits at z >= 1.5
