@@ -124,6 +124,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tuning", type=int, default=0, help="GS_TUNE_* flags (experiments)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -168,7 +169,7 @@ def main():
     host = {k: v.contiguous().float().pin_memory() for k, v in host.items()}
     d = {k: v.to(dev) for k, v in host.items()}
     bs = BatchSettings(image_height=HW, image_width=HW, viewmatrix=d["viewmatrix"], projmatrix=d["projmatrix"],
-                       campos=d["campos"], bg=d["bg"], sh_degree=4, tanfov=d["tanfov"])
+                       campos=d["campos"], bg=d["bg"], sh_degree=4, tanfov=d["tanfov"], tuning=args.tuning)
 
     def fwd():
         with torch.no_grad():
@@ -194,6 +195,7 @@ def main():
     hcfg.P, hcfg.S, hcfg.V, hcfg.M, hcfg.sh_degree = P_GAUSS, 1, VIEWS, D_SH, 4
     hcfg.image_height = hcfg.image_width = HW
     hcfg.scale_modifier = 1.0
+    hcfg.tuning = args.tuning
     for k in ("viewmatrix", "projmatrix", "campos", "bg", "tanfov"):
         setattr(hcfg, k, host[k].data_ptr())
     hin = _capi.GsInputs(means3D=host["means3D"].data_ptr(), opacities=host["opacities"].data_ptr(),

@@ -118,20 +118,22 @@ struct ViewCam {
     float bg[3];
 };
 
-__device__ __forceinline__ void load_view_cam(const DevCfg &c, int v, ViewCam *cam) {
-    // called by all threads of the block; followed by __syncthreads() at the call site
-    int t = threadIdx.x + threadIdx.y * blockDim.x;
-    if (t < 16) {
-        cam->view[t] = c.view[v * 16 + t];
-        cam->proj[t] = c.proj[v * 16 + t];
-    } else if (t < 19) {
-        cam->campos[t - 16] = c.campos[v * 3 + (t - 16)];
-    } else if (t < 22) {
-        cam->bg[t - 19] = c.bg ? c.bg[v * 3 + (t - 19)] : 0.0f;
-    } else if (t == 22) {
-        cam->tanfovx = c.tanfov ? c.tanfov[v * 2 + 0] : c.tanfovx;
-        cam->tanfovy = c.tanfov ? c.tanfov[v * 2 + 1] : c.tanfovy;
-        cam->scale = c.view_scale ? c.view_scale[v] : 1.0f;
+#define GS_CAM_CHUNK 8  // cameras staged per barrier by the per-Gaussian kernels
+
+// Stages cameras [v0, v0+count) into cams[0..count): called by all threads of the block, followed by
+// __syncthreads() at the call site.  One barrier pair per GS_CAM_CHUNK views instead of per view.
+__device__ __forceinline__ void load_view_cams(const DevCfg &c, int v0, int count, ViewCam *cams) {
+    const int nthreads = blockDim.x * blockDim.y;
+    for (int t = threadIdx.x + threadIdx.y * blockDim.x; t < count * 41; t += nthreads) {
+        const int k = t / 41, f = t - k * 41, v = v0 + k;
+        ViewCam *cam = cams + k;
+        if (f < 16) cam->view[f] = c.view[v * 16 + f];
+        else if (f < 32) cam->proj[f - 16] = c.proj[v * 16 + (f - 16)];
+        else if (f < 35) cam->campos[f - 32] = c.campos[v * 3 + (f - 32)];
+        else if (f < 38) cam->bg[f - 35] = c.bg ? c.bg[v * 3 + (f - 35)] : 0.0f;
+        else if (f == 38) cam->tanfovx = c.tanfov ? c.tanfov[v * 2 + 0] : c.tanfovx;
+        else if (f == 39) cam->tanfovy = c.tanfov ? c.tanfov[v * 2 + 1] : c.tanfovy;
+        else cam->scale = c.view_scale ? c.view_scale[v] : 1.0f;
     }
 }
 

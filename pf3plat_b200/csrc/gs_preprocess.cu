@@ -16,9 +16,10 @@ namespace {
 constexpr int PRE_THREADS = 128;
 
 struct PreSmem {
-    ViewCam cam;
+    ViewCam cams[GS_CAM_CHUNK];
     uint64_t bar;
 };
+constexpr int PRE_SMEM_HDR = (sizeof(PreSmem) + 127) / 128 * 128;
 
 __device__ __forceinline__ float3 eval_sh(int deg, const float *sh /* [M][3] for this Gaussian */, float3 dir,
                                           uint32_t &clamped) {
@@ -146,7 +147,7 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
              ushort4 *__restrict__ rects, uint32_t *__restrict__ tile_counts) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PreSmem *sm = reinterpret_cast<PreSmem *>(smem_raw);
-    float *sh_s = reinterpret_cast<float *>(smem_raw + 256);  // PreSmem fits in 256 bytes
+    float *sh_s = reinterpret_cast<float *>(smem_raw + PRE_SMEM_HDR);
 
     const int scene = blockIdx.y;
     const int g0 = blockIdx.x * PRE_THREADS;
@@ -195,37 +196,40 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
         if (bulk) mbar_wait(&sm->bar, 0);
     }
 
-    for (int vi = 0; vi < c.VPS; vi++) {
-        const int v = scene * c.VPS + vi;
+    for (int v0 = 0; v0 < c.VPS; v0 += GS_CAM_CHUNK) {
+        const int nv = min(GS_CAM_CHUNK, c.VPS - v0);
         __syncthreads();
-        load_view_cam(c, v, &sm->cam);
+        load_view_cams(c, scene * c.VPS + v0, nv, sm->cams);
         __syncthreads();
         if (!active) continue;
-        const size_t o = (size_t)v * c.P + i;
-        Splat sp;
-        project_splat<HAS_SH>(c, sm->cam, mean, c6, opac, sh_s + (size_t)tid * c.M * 3,
-                              HAS_SH ? nullptr : in.colors_precomp + o * 3, sp);
-        if (sp.radius > 0) {
-            rec0[o] = sp.r0;
-            rec1[o] = sp.r1;
-            rec2[o] = sp.r2;
+        for (int vi = 0; vi < nv; vi++) {
+            const int v = scene * c.VPS + v0 + vi;
+            const size_t o = (size_t)v * c.P + i;
+            Splat sp;
+            project_splat<HAS_SH>(c, sm->cams[vi], mean, c6, opac, sh_s + (size_t)tid * c.M * 3,
+                                  HAS_SH ? nullptr : in.colors_precomp + o * 3, sp);
+            if (sp.radius > 0) {
+                rec0[o] = sp.r0;
+                rec1[o] = sp.r1;
+                rec2[o] = sp.r2;
+            }
+            radii[o] = sp.radius;
+            rects[o] = sp.rect;
+            // count this Gaussian into every (view, tile) list it will join (binning step 1: RED.ADD, no return;
+            // sub-counter i % BIN_SUB, one counter per 32-byte sector -- see gs_binning.cu)
+            for (int ty = sp.rect.y; ty < sp.rect.w; ty++)
+                for (int tx = sp.rect.x; tx < sp.rect.z; tx++)
+                    atomicAdd(&tile_counts[(((size_t)v * c.ntiles + ty * c.gx + tx) * BIN_SUB + (i & (BIN_SUB - 1))) * BIN_PAD],
+                              1u);
+            meta[o] = (uint8_t)sp.meta;
         }
-        radii[o] = sp.radius;
-        rects[o] = sp.rect;
-        // count this Gaussian into every (view, tile) list it will join (binning step 1: RED.ADD, no return;
-        // sub-counter i % BIN_SUB, one counter per 32-byte sector -- see gs_binning.cu)
-        for (int ty = sp.rect.y; ty < sp.rect.w; ty++)
-            for (int tx = sp.rect.x; tx < sp.rect.z; tx++)
-                atomicAdd(&tile_counts[(((size_t)v * c.ntiles + ty * c.gx + tx) * BIN_SUB + (i & (BIN_SUB - 1))) * BIN_PAD],
-                          1u);
-        meta[o] = (uint8_t)sp.meta;
     }
 }
 
 __global__ void k_mark_visible(const DevCfg c, const float *__restrict__ means3D, uint8_t *__restrict__ present) {
     __shared__ ViewCam cam;
     const int v = blockIdx.y;
-    load_view_cam(c, v, &cam);
+    load_view_cams(c, v, 1, &cam);
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.P) return;
@@ -242,11 +246,11 @@ int launch_preprocess(const DevCfg &c, const DevInputs &in, float4 *rec0, float4
     if (c.P == 0) return GS_OK;
     dim3 grid((c.P + PRE_THREADS - 1) / PRE_THREADS, c.S);
     if (in.shs) {
-        size_t smem = 256 + (size_t)PRE_THREADS * c.M * 12;
+        size_t smem = PRE_SMEM_HDR + (size_t)PRE_THREADS * c.M * 12;
         GS_CUDA_OK(cudaFuncSetAttribute(k_preprocess<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_preprocess<true><<<grid, PRE_THREADS, smem, st>>>(c, in, rec0, rec1, rec2, meta, radii, rects, tile_counts);
     } else {
-        k_preprocess<false><<<grid, PRE_THREADS, 256, st>>>(c, in, rec0, rec1, rec2, meta, radii, rects, tile_counts);
+        k_preprocess<false><<<grid, PRE_THREADS, PRE_SMEM_HDR, st>>>(c, in, rec0, rec1, rec2, meta, radii, rects, tile_counts);
     }
     GS_CUDA_OK(cudaGetLastError());
     return GS_OK;

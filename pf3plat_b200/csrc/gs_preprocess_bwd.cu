@@ -16,11 +16,16 @@ namespace {
 constexpr int PB_THREADS = 128;
 
 struct PbSmem {
-    ViewCam cam;
+    ViewCam cams[GS_CAM_CHUNK];
     uint64_t bar;
 };
+constexpr int PB_SMEM_HDR = (sizeof(PbSmem) + 127) / 128 * 128;
 
-// dL/dsh_k = basis_k(dir) * g  and  dL/ddir, for one colour channel (sh, gsh: stride-3 arrays of this channel)
+constexpr int PB_SH_EVAL = 16;  // coefficients per channel the evaluator can touch (bands 0..3)
+
+// dL/dsh_k += basis_k(dir) * g  and  dL/ddir, for one colour channel.  sh: stride-3 view of this channel's
+// coefficients in shared memory; gsh: stride-3 view of this channel's accumulators (REGISTERS: all indices are
+// compile-time constants after inlining).
 __device__ __forceinline__ void sh_backward_channel(int deg, const float *sh, float *gsh, float g, float x, float y,
                                                     float z, float &ddx, float &ddy, float &ddz) {
     gsh[0 * 3] += GS_SH_C0 * g;
@@ -73,8 +78,7 @@ k_preprocess_bwd(const DevCfg c, const DevInputs in, const uint8_t *__restrict__
                  const GsInGrads g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PbSmem *sm = reinterpret_cast<PbSmem *>(smem_raw);
-    float *sh_s = reinterpret_cast<float *>(smem_raw + 256);
-    float *gsh_s = sh_s + (HAS_SH ? (size_t)PB_THREADS * c.M * 3 : 0);
+    float *sh_s = reinterpret_cast<float *>(smem_raw + PB_SMEM_HDR);
 
     const int scene = blockIdx.y;
     const int g0 = blockIdx.x * PB_THREADS;
@@ -101,8 +105,10 @@ k_preprocess_bwd(const DevCfg c, const DevInputs in, const uint8_t *__restrict__
         } else {
             for (uint32_t k = tid; k < sh_floats; k += PB_THREADS) sh_s[k] = src[k];
         }
-        for (uint32_t k = tid; k < sh_floats; k += PB_THREADS) gsh_s[k] = 0.f;
     }
+    float gsh[PB_SH_EVAL * 3];
+#pragma unroll
+    for (int k = 0; k < PB_SH_EVAL * 3; k++) gsh[k] = 0.f;
 
     float3 mean = make_float3(0, 0, 0);
     float c6[6] = {0, 0, 0, 0, 0, 0};
@@ -129,11 +135,13 @@ k_preprocess_bwd(const DevCfg c, const DevInputs in, const uint8_t *__restrict__
 
     for (int vi = 0; vi < c.VPS; vi++) {
         const int v = scene * c.VPS + vi;
-        __syncthreads();
-        load_view_cam(c, v, &sm->cam);
-        __syncthreads();
+        if (vi % GS_CAM_CHUNK == 0) {
+            __syncthreads();
+            load_view_cams(c, v, min(GS_CAM_CHUNK, c.VPS - vi), sm->cams);
+            __syncthreads();
+        }
         if (!active) continue;
-        const ViewCam &cam = sm->cam;
+        const ViewCam &cam = sm->cams[vi % GS_CAM_CHUNK];
         const size_t o = (size_t)v * c.P + i;
         const uint32_t mb = meta[o];
         float m2d[2] = {0.f, 0.f}, gcol[3] = {0.f, 0.f, 0.f};
@@ -217,7 +225,6 @@ k_preprocess_bwd(const DevCfg c, const DevInputs in, const uint8_t *__restrict__
                 const float x = d[0] * inv, y = d[1] * inv, z = d[2] * inv;
                 float ddx = 0.f, ddy = 0.f, ddz = 0.f;
                 const float *sh = sh_s + (size_t)tid * c.M * 3;
-                float *gsh = gsh_s + (size_t)tid * c.M * 3;
 #pragma unroll
                 for (int ch = 0; ch < 3; ch++) {
                     const float gch = (mb & (1u << ch)) ? 0.0f : gcol[ch];
@@ -290,17 +297,28 @@ k_preprocess_bwd(const DevCfg c, const DevInputs in, const uint8_t *__restrict__
     }
 
     if (HAS_SH && g.dL_dshs) {
+        // the staged input block is dead now: overwrite it with the gradient block (zeros beyond the evaluated
+        // bands) and send it out with one bulk store
         float *dst = g.dL_dshs + ((size_t)scene * c.P + g0) * c.M * 3;
+        __syncthreads();  // every thread has finished reading sh_s
+        if (active) {
+            float *row = sh_s + (size_t)tid * c.M * 3;
+            const int used = min(c.M, PB_SH_EVAL) * 3;
+#pragma unroll
+            for (int k = 0; k < PB_SH_EVAL * 3; k++)
+                if (k < used) row[k] = gsh[k];
+            for (int k = used; k < c.M * 3; k++) row[k] = 0.f;
+        }
         if (bulk) {
             fence_proxy_async_smem();  // make the generic-proxy smem writes visible to the TMA engine
             __syncthreads();
             if (tid == 0) {
-                tma_store_1d(dst, gsh_s, sh_floats * 4u);
+                tma_store_1d(dst, sh_s, sh_floats * 4u);
                 tma_store_commit_wait();
             }
         } else {
             __syncthreads();
-            for (uint32_t k = tid; k < sh_floats; k += PB_THREADS) dst[k] = gsh_s[k];
+            for (uint32_t k = tid; k < sh_floats; k += PB_THREADS) dst[k] = sh_s[k];
         }
     }
 }
@@ -312,11 +330,11 @@ int launch_preprocess_bwd(const DevCfg &c, const DevInputs &in, const GsSaved &s
     if (c.P == 0) return GS_OK;
     dim3 grid((c.P + PB_THREADS - 1) / PB_THREADS, c.S);
     if (in.shs) {
-        size_t smem = 256 + 2 * (size_t)PB_THREADS * c.M * 12;
+        size_t smem = PB_SMEM_HDR + (size_t)PB_THREADS * c.M * 12;
         GS_CUDA_OK(cudaFuncSetAttribute(k_preprocess_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_preprocess_bwd<true><<<grid, PB_THREADS, smem, st>>>(c, in, s.meta, grad_acc, g);
     } else {
-        k_preprocess_bwd<false><<<grid, PB_THREADS, 256, st>>>(c, in, s.meta, grad_acc, g);
+        k_preprocess_bwd<false><<<grid, PB_THREADS, PB_SMEM_HDR, st>>>(c, in, s.meta, grad_acc, g);
     }
     GS_CUDA_OK(cudaGetLastError());
     return GS_OK;
