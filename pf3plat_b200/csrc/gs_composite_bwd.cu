@@ -45,23 +45,24 @@ struct PixState {
 
 // Returns whether this pixel received the Gaussian (and hence wrote non-trivial partial gradients to g).
 template <bool DEPTH>
-__device__ __forceinline__ bool pixel_grad(PixState &ps, bool live, float4 q0, float4 q1, float4 q2, float pxf,
-                                           float pyf, float half_w, float half_h, float *g /* [GS_ACC_STRIDE] */) {
+__device__ __forceinline__ bool pixel_grad(PixState &ps, bool live, uint32_t rec_addr, float pxf, float pyf,
+                                           float half_w, float half_h, float *g /* [GS_ACC_STRIDE] */) {
 #pragma unroll
     for (int k = 0; k < GS_ACC_STRIDE; k++) g[k] = 0.f;
-    if (!live) return false;
+    const float4 q0 = lds128(rec_addr), q1 = lds128(rec_addr + 16u);
     const float dx = q0.x - pxf, dy = q0.y - pyf;
     const float p2 = gs_power2(q0.z, q0.w, q1.x, dx, dy);
-    if (p2 > 0.0f) return false;
     const float G = gs_ex2(p2);
     const float alpha = fminf(GS_ALPHA_MAX, q1.y * G);
-    if (alpha < GS_ALPHA_MIN) return false;
+    // one divergent region: the test above is evaluated by all lanes unconditionally
+    if (!(live && p2 <= 0.0f && alpha >= GS_ALPHA_MIN)) return false;
+    const float2 q2 = lds64(rec_addr + 32u);
     // one approximate reciprocal (MUFU.RCP, <= 1 ulp) serves both divisions by (1 - alpha); the IEEE divisions
     // upstream uses cost ~10 instructions each and the 1e-3 gradient tolerance does not need them
     const float inv_1ma = gs_rcp(1.0f - alpha);
     ps.T = ps.T * inv_1ma;
     const float w = alpha * ps.T;
-    const float col[3] = {q1.z, q1.w, q2.x};
+    const float col[3] = {q1.z, q1.w, q2.x};  // q2 = (b, z)
     float dL_dalpha = 0.f;
 #pragma unroll
     for (int ch = 0; ch < 3; ch++) {
@@ -101,7 +102,8 @@ k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
                 const uint2 *__restrict__ ranges, const float *__restrict__ final_T,
                 const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dcolor,
                 const float *__restrict__ dL_ddepth, float *__restrict__ acc) {
-    __shared__ float4 s0[CB_BATCH], s1[CB_BATCH], s2[CB_BATCH];
+    __shared__ float4 s_box[CB_BATCH];     // (x, y, hx, hy) per Gaussian: read by lane k for Gaussian k
+    __shared__ float4 s_rec[CB_BATCH][3];  // rec0 | rec1 | rec2, read as warp-wide broadcasts
     __shared__ uint32_t sid[CB_BATCH];
     __shared__ uint32_t s_max[CB_THREADS / 32];
 
@@ -113,8 +115,9 @@ k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
     const int px = bx + (lane & 7), py = by + (lane >> 3);
     const bool inside = px < c.W && py < c.H;
     const float pxf = (float)px, pyf = (float)py;
-    const float bx0 = (float)bx, bx1 = (float)(bx + 7), by0 = (float)by, by1 = (float)(by + 3);
+    const float bcx = (float)bx + 3.5f, bcy = (float)by + 1.5f;  // block centre (half size 3.5 x 1.5)
     const float half_w = 0.5f * (float)c.W, half_h = 0.5f * (float)c.H;
+    const uint32_t box_addr = smem_u32(&s_box[0]), rec_addr = smem_u32(&s_rec[0][0]);
 
     const uint2 range = ranges[(size_t)v * c.ntiles + tile];
     const size_t rbase = (size_t)v * c.P;
@@ -158,10 +161,12 @@ k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
         if ((uint32_t)tid < nb) {
             const uint32_t id = point_list[range.x + lo + tid];
             const size_t r = rbase + id;
+            const float4 q0 = rec0[r], q1 = rec1[r], q2 = rec2[r];
             sid[tid] = id;
-            s0[tid] = rec0[r];
-            s1[tid] = rec1[r];
-            s2[tid] = rec2[r];
+            s_box[tid] = make_float4(q0.x, q0.y, q2.z, q2.w);
+            s_rec[tid][0] = q0;
+            s_rec[tid][1] = q1;
+            s_rec[tid][2] = q2;
         }
         __syncthreads();
         if (lo >= warp_last) continue;  // nothing in this batch is below any of this warp's last contributors
@@ -169,8 +174,8 @@ k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
             const uint32_t j = (uint32_t)chunk + lane;
             bool hit = false;
             if (j < nb && lo + j < warp_last) {
-                const float4 a = s0[j], e = s2[j];
-                hit = (a.x + e.z >= bx0) && (a.x - e.z <= bx1) && (a.y + e.w >= by0) && (a.y - e.w <= by1);
+                const float4 bb = lds128(box_addr + j * 16u);
+                hit = (fabsf(bb.x - bcx) <= bb.z + 3.5f) && (fabsf(bb.y - bcy) <= bb.w + 1.5f);
             }
             uint32_t mask = __ballot_sync(0xffffffffu, hit);
             while (mask) {
@@ -185,7 +190,7 @@ k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
                         mask &= ~(1u << b);
                         const uint32_t jj = (uint32_t)chunk + b;
                         gid[slot] = sid[jj];
-                        any_got |= pixel_grad<DEPTH>(ps, lo + jj < ps.last, s0[jj], s1[jj], s2[jj], pxf, pyf, half_w,
+                        any_got |= pixel_grad<DEPTH>(ps, lo + jj < ps.last, rec_addr + jj * 48u, pxf, pyf, half_w,
                                                      half_h, g);
                     } else {
                         gid[slot] = 0xffffffffu;

@@ -18,13 +18,19 @@ namespace {
 constexpr int CF_THREADS = 256;
 constexpr int CF_BATCH = 256;
 
+// Shared-memory staging of one batch: per Gaussian a 16-byte cull box and a 48-byte evaluation record.
+struct CfBatch {
+    float4 box[CF_BATCH];      // (x, y, hx, hy): read by lane k for Gaussian k (conflict-free LDS.128)
+    float4 rec[CF_BATCH][3];   // rec0 | rec1 | rec2 of gs_common.cuh, read as warp-wide broadcasts
+};
+
 template <bool DEPTH>
 __global__ void __launch_bounds__(CF_THREADS)
 k_composite_fwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *__restrict__ rec1,
                 const float4 *__restrict__ rec2, const uint32_t *__restrict__ point_list,
                 const uint2 *__restrict__ ranges, float *__restrict__ color, float *__restrict__ depth,
                 float *__restrict__ final_T, uint32_t *__restrict__ n_contrib) {
-    __shared__ float4 s0[CF_BATCH], s1[CF_BATCH], s2[CF_BATCH];
+    __shared__ CfBatch sm;
 
     const int v = blockIdx.y;
     const int tile = blockIdx.x;
@@ -34,10 +40,12 @@ k_composite_fwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
     const int px = bx + (lane & 7), py = by + (lane >> 3);
     const bool inside = px < c.W && py < c.H;
     const float pxf = (float)px, pyf = (float)py;
-    const float bx0 = (float)bx, bx1 = (float)(bx + 7), by0 = (float)by, by1 = (float)(by + 3);
+    // block centre and half size: the cull test is |x - cx| <= hx + 3.5 && |y - cy| <= hy + 1.5
+    const float bcx = (float)bx + 3.5f, bcy = (float)by + 1.5f;
 
     const uint2 range = ranges[(size_t)v * c.ntiles + tile];
     const size_t rbase = (size_t)v * c.P;
+    const uint32_t box_addr = smem_u32(&sm.box[0]), rec_addr = smem_u32(&sm.rec[0][0]);
 
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dz = 0.f;
     uint32_t last = 0;
@@ -49,44 +57,48 @@ k_composite_fwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
         const uint32_t nb = min((uint32_t)CF_BATCH, range.y - base);
         if ((uint32_t)tid < nb) {
             const size_t r = rbase + point_list[base + tid];
-            s0[tid] = rec0[r];
-            s1[tid] = rec1[r];
-            s2[tid] = rec2[r];
+            const float4 q0 = rec0[r], q1 = rec1[r], q2 = rec2[r];
+            sm.box[tid] = make_float4(q0.x, q0.y, q2.z, q2.w);
+            sm.rec[tid][0] = q0;
+            sm.rec[tid][1] = q1;
+            sm.rec[tid][2] = q2;
         }
         __syncthreads();
         if (warp_done) continue;
+        const uint32_t pos0 = base - range.x + 1;  // 1-based list position of this batch's first entry
         for (uint32_t chunk = 0; chunk < nb; chunk += 32) {
             const uint32_t j = chunk + lane;
             bool hit = false;
             if (j < nb) {
-                const float4 a = s0[j], e = s2[j];
-                hit = (a.x + e.z >= bx0) && (a.x - e.z <= bx1) && (a.y + e.w >= by0) && (a.y - e.w <= by1);
+                const float4 bb = lds128(box_addr + j * 16u);
+                hit = (fabsf(bb.x - bcx) <= bb.z + 3.5f) && (fabsf(bb.y - bcy) <= bb.w + 1.5f);
             }
             uint32_t mask = __ballot_sync(0xffffffffu, hit);
+            const uint32_t chunk_addr = rec_addr + chunk * 48u;
             while (mask) {
-                const int b = __ffs(mask) - 1;
-                mask &= mask - 1;
-                if (done) continue;
-                const uint32_t jj = chunk + b;
-                const float4 q0 = s0[jj], q1 = s1[jj];
+                const uint32_t b = (uint32_t)__ffs(mask) - 1u;
+                mask &= mask - 1u;
+                const uint32_t a = chunk_addr + b * 48u;
+                const float4 q0 = lds128(a), q1 = lds128(a + 16u);
                 const float dx = q0.x - pxf, dy = q0.y - pyf;
                 const float p2 = gs_power2(q0.z, q0.w, q1.x, dx, dy);
-                if (p2 > 0.0f) continue;
                 const float alpha = fminf(GS_ALPHA_MAX, q1.y * gs_ex2(p2));
-                if (alpha < GS_ALPHA_MIN) continue;
-                const float test_T = T * (1.0f - alpha);
-                if (test_T < GS_T_MIN) {
-                    done = true;
-                    continue;
+                // one divergent region: everything above is evaluated by all lanes unconditionally
+                if (!done && p2 <= 0.0f && alpha >= GS_ALPHA_MIN) {
+                    const float test_T = T * (1.0f - alpha);
+                    if (test_T < GS_T_MIN) {
+                        done = true;
+                    } else {
+                        const float2 q2 = lds64(a + 32u);
+                        const float w = alpha * T;
+                        C0 = fmaf(q1.z, w, C0);
+                        C1 = fmaf(q1.w, w, C1);
+                        C2 = fmaf(q2.x, w, C2);
+                        if (DEPTH) Dz = fmaf(q2.y, w, Dz);
+                        T = test_T;
+                        last = pos0 + chunk + b;
+                    }
                 }
-                const float4 q2 = s2[jj];
-                const float w = alpha * T;
-                C0 += q1.z * w;
-                C1 += q1.w * w;
-                C2 += q2.x * w;
-                if (DEPTH) Dz += q2.y * w;
-                T = test_T;
-                last = base - range.x + jj + 1;
             }
             if (__all_sync(0xffffffffu, done)) {
                 warp_done = true;
