@@ -174,8 +174,14 @@ GS_API int gs_get_stats(const GsContext *ctx, GsStats *out);
 GS_API int gs_render_host(GsContext *ctx, const GsConfig *cfg, const GsInputs *in, const GsOutputs *out, void *stream);
 
 /* Per-stage device timings (ms) of the last forward/backward when profiling is enabled; CUDA events on `stream`. */
-enum { GS_STAGE_PREPROCESS = 0, GS_STAGE_BIN = 1, GS_STAGE_COMPOSITE = 2, GS_STAGE_COMPOSITE_BWD = 3,
-       GS_STAGE_PREPROCESS_BWD = 4, GS_NUM_STAGES = 5 };
+enum { GS_STAGE_PREPROCESS = 0,      /* k_preprocess (incl. tile counting) */
+       GS_STAGE_BIN_SCAN = 1,        /* k_tile_scan + the forward's one host read-back */
+       GS_STAGE_BIN_EMIT = 2,        /* k_emit_buckets (or the radix fallback's whole chain) */
+       GS_STAGE_BIN_SORT = 3,        /* k_tile_sort */
+       GS_STAGE_COMPOSITE = 4,       /* k_composite_fwd */
+       GS_STAGE_COMPOSITE_BWD = 5,   /* accumulator memset + k_composite_bwd */
+       GS_STAGE_PREPROCESS_BWD = 6,  /* k_preprocess_bwd */
+       GS_NUM_STAGES = 7 };
 GS_API int gs_set_profiling(GsContext *ctx, int enabled);
 GS_API int gs_get_stage_ms(GsContext *ctx, float *ms /* [GS_NUM_STAGES] */);
 

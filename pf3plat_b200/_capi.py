@@ -17,8 +17,8 @@ ABI_VERSION = 1
 GS_FLAG_DEPTH = 1
 GS_FLAG_PREFILTERED = 2
 GS_TUNE_FORCE_RADIX_BINNING = 1
-GS_NUM_STAGES = 5
-STAGE_NAMES = ("preprocess", "bin", "composite", "composite_bwd", "preprocess_bwd")
+GS_NUM_STAGES = 7
+STAGE_NAMES = ("preprocess", "bin_scan", "bin_emit", "bin_sort", "composite", "composite_bwd", "preprocess_bwd")
 
 
 class GsConfig(Structure):

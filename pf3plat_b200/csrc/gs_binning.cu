@@ -23,6 +23,7 @@
 // The block-level merge sort, the device scan and the device radix sorts are CUB primitives (library code, like
 // cuBLAS for a plain GEMM); the count / scan / emit / range kernels are ours.
 #include <cub/cub.cuh>
+#include <thrust/iterator/transform_iterator.h>
 
 #include "gs_common.cuh"
 
@@ -204,7 +205,7 @@ int tile_bits(const DevCfg &c) {
 size_t cub_temp_bytes(const DevCfg &c, int64_t n, int64_t D) {
     size_t t1 = 0, t2 = 0, t3 = 0;
     cub::DeviceRadixSort::SortKeys(nullptr, t1, (const uint64_t *)nullptr, (uint64_t *)nullptr, (int)n, 32, 64);
-    cub::TransformInputIterator<uint32_t, TilesInOrder, const uint64_t *> it(nullptr, TilesInOrder{nullptr});
+    auto it = thrust::make_transform_iterator((const uint64_t *)nullptr, TilesInOrder{nullptr});
     cub::DeviceScan::InclusiveSum(nullptr, t2, it, (uint32_t *)nullptr, (int)n);
     cub::DeviceRadixSort::SortPairs(nullptr, t3, (const uint32_t *)nullptr, (uint32_t *)nullptr,
                                     (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)D, 0, tile_bits(c));
@@ -232,17 +233,21 @@ size_t bin_scratch_bytes(const DevCfg &c, int64_t D, bool fast) {
     return 2 * align256(n * 8) + align256(n * 4) + 3 * align256((size_t)D * 4) + cub_temp_bytes(c, (int64_t)n, D);
 }
 
-int bin_sort_fast(const DevCfg &c, int64_t D, uint32_t max_count, const float4 *rec2, const ushort4 *rects,
-                  const uint32_t *offsets, const uint32_t *tile_start, const uint32_t *tile_n, uint32_t *cursor,
-                  void *scratch, uint32_t *point_list, uint2 *ranges, cudaStream_t st) {
+int bin_emit_fast(const DevCfg &c, int64_t D, const float4 *rec2, const ushort4 *rects, const uint32_t *offsets,
+                  uint32_t *cursor, void *scratch, cudaStream_t st) {
+    if (D <= 0) return GS_OK;
+    GS_CUDA_OK(cudaMemsetAsync(cursor, 0, bin_counter_bytes(c), st));
+    const size_t n = (size_t)c.V * c.P;
+    k_emit_buckets<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c, rec2, rects, offsets, cursor,
+                                                                 static_cast<uint64_t *>(scratch));
+    GS_CUDA_OK(cudaGetLastError());
+    return GS_OK;
+}
+
+int bin_sort_fast(const DevCfg &c, uint32_t max_count, const uint32_t *tile_start, const uint32_t *tile_n,
+                  const void *scratch, uint32_t *point_list, uint2 *ranges, cudaStream_t st) {
     const int nvt = c.V * c.ntiles;
-    uint64_t *bucket = static_cast<uint64_t *>(scratch);
-    if (D > 0) {
-        GS_CUDA_OK(cudaMemsetAsync(cursor, 0, bin_counter_bytes(c), st));
-        const size_t n = (size_t)c.V * c.P;
-        k_emit_buckets<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c, rec2, rects, offsets, cursor, bucket);
-        GS_CUDA_OK(cudaGetLastError());
-    }
+    const uint64_t *bucket = static_cast<const uint64_t *>(scratch);
     if (max_count <= TS_THREADS * 2) return launch_tile_sort<2>(nvt, tile_n, tile_start, bucket, point_list, ranges, st);
     if (max_count <= TS_THREADS * 8) return launch_tile_sort<8>(nvt, tile_n, tile_start, bucket, point_list, ranges, st);
     if (max_count <= TS_THREADS * 16) return launch_tile_sort<16>(nvt, tile_n, tile_start, bucket, point_list, ranges, st);
@@ -272,7 +277,7 @@ int bin_sort_fallback(const DevCfg &c, int64_t D, const float4 *rec2, const usho
     k_depth_keys<<<blocks, 256, 0, st>>>(n, rec2, rects, depth_keys);
     GS_CUDA_OK(cudaGetLastError());
     GS_CUDA_OK(cub::DeviceRadixSort::SortKeys(p, temp_bytes, depth_keys, order, (int)n, 32, 64, st));
-    cub::TransformInputIterator<uint32_t, TilesInOrder, const uint64_t *> it(order, TilesInOrder{rects});
+    auto it = thrust::make_transform_iterator((const uint64_t *)order, TilesInOrder{rects});
     GS_CUDA_OK(cub::DeviceScan::InclusiveSum(p, temp_bytes, it, offsets, (int)n, st));
     k_emit_ordered<<<blocks, 256, 0, st>>>(c, order, rects, offsets, keys_in, vals_in);
     GS_CUDA_OK(cudaGetLastError());

@@ -299,15 +299,16 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     }
 
     int64_t D = 0;
+    uint32_t max_count = 0;
     {
-        StageTimer t(ctx, GS_STAGE_BIN, st);
+        StageTimer t(ctx, GS_STAGE_BIN_SCAN, st);
         rc = bin_tile_scan(c, tile_counts, sub_offsets, tile_start, tile_n, info, st);
         if (rc != GS_OK) return fail(rc);
         cudaError_t e = cudaMemcpyAsync(ctx->h_word, info, 8, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the one host sync of the forward
         if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "read back num_rendered", __FILE__, __LINE__));
         D = (int64_t)ctx->h_word[0];
-        const uint32_t max_count = ctx->h_word[1];
+        max_count = ctx->h_word[1];
         if (ctx->host_radii_dst && ctx->copy_stream) {  // preprocess has completed: radii can leave now
             e = cudaMemcpyAsync(ctx->host_radii_dst, out->radii, ctx->host_radii_bytes, cudaMemcpyDeviceToHost,
                                 ctx->copy_stream);
@@ -321,19 +322,23 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
             return fail(gs_set_cuda_error(e, "cudaMallocAsync(point_list)", __FILE__, __LINE__));
         }
         s->D = D;
-        const bool fast = bin_fits_fast_path(max_count) && !(cfg->tuning & GS_TUNE_FORCE_RADIX_BINNING);
-        rc = ctx->sort.reserve(bin_scratch_bytes(c, D, fast), 1.25);
-        if (rc == GS_OK) {
-            if (fast)
-                rc = bin_sort_fast(c, D, max_count, s->rec2, rects, sub_offsets, tile_start, tile_n, cursor, ctx->sort.p,
-                                   s->point_list, s->ranges, st);
-            else
-                rc = bin_sort_fallback(c, D, s->rec2, rects, ctx->sort.p, ctx->sort.bytes, s->point_list, s->ranges, st);
-        }
-        if (rc != GS_OK) return fail(rc);
-        ctx->stats.kernel_launches += 1 + (D > 0 ? 1 : 0) + 1;  // scan, emit, tile sort (fallback: 3 + CUB's)
-        ctx->stats.max_tile_list = (int32_t)max_count;
     }
+    const bool fast = bin_fits_fast_path(max_count) && !(cfg->tuning & GS_TUNE_FORCE_RADIX_BINNING);
+    rc = ctx->sort.reserve(bin_scratch_bytes(c, D, fast), 1.25);
+    if (rc != GS_OK) return fail(rc);
+    {
+        StageTimer t(ctx, GS_STAGE_BIN_EMIT, st);
+        if (fast) rc = bin_emit_fast(c, D, s->rec2, rects, sub_offsets, cursor, ctx->sort.p, st);
+        else rc = bin_sort_fallback(c, D, s->rec2, rects, ctx->sort.p, ctx->sort.bytes, s->point_list, s->ranges, st);
+        if (rc != GS_OK) return fail(rc);
+    }
+    if (fast) {
+        StageTimer t(ctx, GS_STAGE_BIN_SORT, st);
+        rc = bin_sort_fast(c, max_count, tile_start, tile_n, ctx->sort.p, s->point_list, s->ranges, st);
+        if (rc != GS_OK) return fail(rc);
+    }
+    ctx->stats.kernel_launches += 1 + (D > 0 ? 1 : 0) + 1;  // scan, emit, tile sort (fallback: 3 + CUB's)
+    ctx->stats.max_tile_list = (int32_t)max_count;
 
     {
         StageTimer t(ctx, GS_STAGE_COMPOSITE, st);

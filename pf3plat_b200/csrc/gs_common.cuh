@@ -69,9 +69,10 @@ int bin_tile_scan(const DevCfg &c, const uint32_t *counters, uint32_t *offsets, 
                   uint32_t *info, cudaStream_t st);
 bool bin_fits_fast_path(uint32_t max_count);
 size_t bin_scratch_bytes(const DevCfg &c, int64_t D, bool fast);
-int bin_sort_fast(const DevCfg &c, int64_t D, uint32_t max_count, const float4 *rec2, const ushort4 *rects,
-                  const uint32_t *offsets, const uint32_t *tile_start, const uint32_t *tile_n, uint32_t *cursor,
-                  void *scratch, uint32_t *point_list, uint2 *ranges, cudaStream_t st);
+int bin_emit_fast(const DevCfg &c, int64_t D, const float4 *rec2, const ushort4 *rects, const uint32_t *offsets,
+                  uint32_t *cursor, void *scratch, cudaStream_t st);
+int bin_sort_fast(const DevCfg &c, uint32_t max_count, const uint32_t *tile_start, const uint32_t *tile_n,
+                  const void *scratch, uint32_t *point_list, uint2 *ranges, cudaStream_t st);
 int bin_sort_fallback(const DevCfg &c, int64_t D, const float4 *rec2, const ushort4 *rects, void *scratch,
                       size_t scratch_bytes, uint32_t *point_list, uint2 *ranges, cudaStream_t st);
 
