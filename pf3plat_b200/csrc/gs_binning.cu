@@ -26,6 +26,7 @@
 #include <thrust/iterator/transform_iterator.h>
 
 #include "gs_common.cuh"
+#include "gs_tile_sort.cuh"
 
 namespace {
 
@@ -98,26 +99,6 @@ __global__ void k_emit_buckets(const DevCfg c, const float4 *__restrict__ rec2, 
         }
 }
 
-constexpr int TS_THREADS = 256;
-
-// 64-bit merge sort of one bucket: (depth_bits << 32 | index) is a total order.
-template <int ITEMS>
-__device__ __forceinline__ void sort_bucket_merge(const uint64_t *__restrict__ src, uint32_t *__restrict__ dst,
-                                                  uint32_t n, void *smem) {
-    using Sort = cub::BlockMergeSort<uint64_t, TS_THREADS, ITEMS>;
-    typename Sort::TempStorage &tmp = *reinterpret_cast<typename Sort::TempStorage *>(smem);
-    uint64_t keys[ITEMS];
-    const uint32_t base = threadIdx.x * ITEMS;
-#pragma unroll
-    for (int k = 0; k < ITEMS; k++) keys[k] = base + k < n ? src[base + k] : ~0ull;
-    Sort(tmp).Sort(keys, [](const uint64_t &a, const uint64_t &b) { return a < b; });
-#pragma unroll
-    for (int k = 0; k < ITEMS; k++)
-        if (base + k < n) dst[base + k] = (uint32_t)keys[k];
-}
-
-// (A 32-bit cub::BlockRadixSort on the depth bits with tie detection was tried in place of the 64-bit merge sort:
-// 6 % slower on the C2 workload, so it was dropped.)
 template <int MAX_ITEMS>
 __global__ void __launch_bounds__(TS_THREADS)
 k_tile_sort(const uint32_t *__restrict__ tile_n, const uint32_t *__restrict__ tile_start,
@@ -129,16 +110,13 @@ k_tile_sort(const uint32_t *__restrict__ tile_n, const uint32_t *__restrict__ ti
     if (n == 0) return;
     const uint64_t *src = bucket + off;
     uint32_t *dst = point_list + off;
-    if (n <= TS_THREADS * 2) sort_bucket_merge<2>(src, dst, n, ts_smem);
-    else if (MAX_ITEMS >= 8 && n <= TS_THREADS * 8) sort_bucket_merge<(MAX_ITEMS >= 8 ? 8 : 2)>(src, dst, n, ts_smem);
-    else if (MAX_ITEMS >= 16 && n <= TS_THREADS * 16) sort_bucket_merge<(MAX_ITEMS >= 16 ? 16 : 2)>(src, dst, n, ts_smem);
-    else sort_bucket_merge<MAX_ITEMS>(src, dst, n, ts_smem);
+    sort_bucket_dispatch<MAX_ITEMS>(src, dst, n, ts_smem);
 }
 
 template <int MAX_ITEMS>
 int launch_tile_sort(int nvt, const uint32_t *counts, const uint32_t *offsets, const uint64_t *bucket,
                      uint32_t *point_list, uint2 *ranges, cudaStream_t st) {
-    const size_t smem = sizeof(typename cub::BlockMergeSort<uint64_t, TS_THREADS, MAX_ITEMS>::TempStorage);
+    const size_t smem = tile_sort_smem_bytes<MAX_ITEMS>();
     GS_CUDA_OK(cudaFuncSetAttribute(k_tile_sort<MAX_ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_tile_sort<MAX_ITEMS><<<nvt, TS_THREADS, smem, st>>>(counts, offsets, bucket, point_list, ranges);
     GS_CUDA_OK(cudaGetLastError());

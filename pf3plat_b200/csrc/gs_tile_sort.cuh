@@ -1,0 +1,41 @@
+// gs_tile_sort.cuh -- shared-memory sort of one (view, tile) bucket, used by k_tile_sort (gs_binning.cu) and by the
+// fused sort+composite forward kernel (gs_composite_fwd.cu).
+#pragma once
+#include <cub/block/block_merge_sort.cuh>
+
+#include "gs_common.cuh"
+
+#define TS_THREADS 256
+
+// Bytes of shared memory sort_bucket_merge<ITEMS> needs.
+template <int ITEMS>
+constexpr size_t tile_sort_smem_bytes() {
+    return sizeof(typename cub::BlockMergeSort<uint64_t, TS_THREADS, ITEMS>::TempStorage);
+}
+
+// 64-bit merge sort of one bucket: (depth_bits << 32 | index) is a total order, so the arbitrary arrival order of
+// the bucket does not matter.  All TS_THREADS threads of the CTA call it; dst receives the indices in order.
+template <int ITEMS>
+__device__ __forceinline__ void sort_bucket_merge(const uint64_t *__restrict__ src, uint32_t *__restrict__ dst,
+                                                  uint32_t n, void *smem) {
+    using Sort = cub::BlockMergeSort<uint64_t, TS_THREADS, ITEMS>;
+    typename Sort::TempStorage &tmp = *reinterpret_cast<typename Sort::TempStorage *>(smem);
+    uint64_t keys[ITEMS];
+    const uint32_t base = threadIdx.x * ITEMS;
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) keys[k] = base + k < n ? src[base + k] : ~0ull;
+    Sort(tmp).Sort(keys, [](const uint64_t &a, const uint64_t &b) { return a < b; });
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++)
+        if (base + k < n) dst[base + k] = (uint32_t)keys[k];
+}
+
+// Sorts a bucket of n <= TS_THREADS * MAX_ITEMS keys with the cheapest instantiation that fits it.
+template <int MAX_ITEMS>
+__device__ __forceinline__ void sort_bucket_dispatch(const uint64_t *__restrict__ src, uint32_t *__restrict__ dst,
+                                                     uint32_t n, void *smem) {
+    if (n <= TS_THREADS * 2) sort_bucket_merge<2>(src, dst, n, smem);
+    else if (MAX_ITEMS >= 8 && n <= TS_THREADS * 8) sort_bucket_merge<(MAX_ITEMS >= 8 ? 8 : 2)>(src, dst, n, smem);
+    else if (MAX_ITEMS >= 16 && n <= TS_THREADS * 16) sort_bucket_merge<(MAX_ITEMS >= 16 ? 16 : 2)>(src, dst, n, smem);
+    else sort_bucket_merge<MAX_ITEMS>(src, dst, n, smem);
+}
