@@ -79,7 +79,8 @@ k_tile_scan(int nvt, const uint32_t *__restrict__ counters, uint32_t *__restrict
     }
 }
 
-__global__ void k_emit_buckets(const DevCfg c, const float4 *__restrict__ rec2, const ushort4 *__restrict__ rects,
+__global__ void k_emit_buckets(const DevCfg c, const float4 *__restrict__ rec0, const float4 *__restrict__ rec1,
+                               const float4 *__restrict__ rec2, const ushort4 *__restrict__ rects,
                                const uint32_t *__restrict__ offsets, uint32_t *__restrict__ cursor,
                                uint64_t *__restrict__ bucket) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -88,11 +89,13 @@ __global__ void k_emit_buckets(const DevCfg c, const float4 *__restrict__ rec2, 
     if (r.z <= r.x || r.w <= r.y) return;
     const uint32_t v = (uint32_t)(g / c.P);
     const uint32_t i = (uint32_t)(g - (size_t)v * c.P);
-    const uint64_t key = ((uint64_t)__float_as_uint(rec2[g].y) << 32) | i;
+    const float4 q0 = rec0[g], q1 = rec1[g], q2 = rec2[g];
+    const uint64_t key = ((uint64_t)__float_as_uint(q2.y) << 32) | i;
     const uint32_t tbase = v * (uint32_t)c.ntiles;
     const uint32_t sub = i & (BIN_SUB - 1);
     for (int y = r.y; y < r.w; y++)
         for (int x = r.x; x < r.z; x++) {
+            if (!gs_tile_reached(q0, q1, q2, x, y)) continue;  // same predicate as the count in k_preprocess
             const size_t slot = (size_t)(tbase + (uint32_t)(y * c.gx + x)) * BIN_SUB + sub;
             const uint32_t pos = atomicAdd(&cursor[slot * BIN_PAD], 1u);
             bucket[(size_t)offsets[slot] + pos] = key;
@@ -126,40 +129,53 @@ int launch_tile_sort(int nvt, const uint32_t *counts, const uint32_t *offsets, c
 // ---------------------------------------------------------------------------------------------------------
 // fallback path (device-wide radix sorts)
 // ---------------------------------------------------------------------------------------------------------
-__device__ __host__ __forceinline__ uint32_t rect_tiles(ushort4 r) {
-    return (r.z > r.x && r.w > r.y) ? (uint32_t)(r.z - r.x) * (uint32_t)(r.w - r.y) : 0u;
+// number of tiles of the candidate rectangle the Gaussian really reaches (the predicate of the fast path)
+__device__ __forceinline__ uint32_t reached_tiles(ushort4 r, float4 q0, float4 q1, float4 q2) {
+    uint32_t n = 0;
+    for (int y = r.y; y < r.w; y++)
+        for (int x = r.x; x < r.z; x++) n += gs_tile_reached(q0, q1, q2, x, y) ? 1u : 0u;
+    return n;
 }
 
-__global__ void k_depth_keys(size_t n, const float4 *__restrict__ rec2, const ushort4 *__restrict__ rects,
-                             uint64_t *__restrict__ keys) {
+__global__ void k_depth_keys(size_t n, const float4 *__restrict__ rec0, const float4 *__restrict__ rec1,
+                             const float4 *__restrict__ rec2, const ushort4 *__restrict__ rects,
+                             uint64_t *__restrict__ keys, uint32_t *__restrict__ cnt) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n) return;
-    // Gaussians without tiles sort to the end (their records were never written)
-    const uint32_t d = rect_tiles(rects[g]) ? __float_as_uint(rec2[g].y) : 0xffffffffu;
+    const ushort4 r = rects[g];
+    uint32_t nt = 0, d = 0xffffffffu;  // Gaussians without tiles sort to the end (their records were never written)
+    if (r.z > r.x && r.w > r.y) {
+        const float4 q2 = rec2[g];
+        nt = reached_tiles(r, rec0[g], rec1[g], q2);
+        if (nt) d = __float_as_uint(q2.y);
+    }
+    cnt[g] = nt;
     keys[g] = ((uint64_t)d << 32) | (uint64_t)g;
 }
 
 struct TilesInOrder {  // tile count gathered through the depth order (input functor of the scan)
-    const ushort4 *rects;
-    __host__ __device__ __forceinline__ uint32_t operator()(const uint64_t &key) const {
-        return rect_tiles(rects[(uint32_t)key]);
-    }
+    const uint32_t *cnt;
+    __host__ __device__ __forceinline__ uint32_t operator()(const uint64_t &key) const { return cnt[(uint32_t)key]; }
 };
 
-__global__ void k_emit_ordered(const DevCfg c, const uint64_t *__restrict__ order, const ushort4 *__restrict__ rects,
+__global__ void k_emit_ordered(const DevCfg c, const uint64_t *__restrict__ order, const float4 *__restrict__ rec0,
+                               const float4 *__restrict__ rec1, const float4 *__restrict__ rec2,
+                               const ushort4 *__restrict__ rects, const uint32_t *__restrict__ cnt,
                                const uint32_t *__restrict__ offsets, uint32_t *__restrict__ keys,
                                uint32_t *__restrict__ vals) {
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= (size_t)c.V * c.P) return;
     const uint32_t g = (uint32_t)order[j];
+    if (cnt[g] == 0) return;
     const ushort4 r = rects[g];
-    if (rect_tiles(r) == 0) return;
+    const float4 q0 = rec0[g], q1 = rec1[g], q2 = rec2[g];
     uint32_t off = j == 0 ? 0u : offsets[j - 1];
     const uint32_t v = g / (uint32_t)c.P;
     const uint32_t i = g - v * (uint32_t)c.P;
     const uint32_t tbase = v * (uint32_t)c.ntiles;
     for (int y = r.y; y < r.w; y++)
         for (int x = r.x; x < r.z; x++) {
+            if (!gs_tile_reached(q0, q1, q2, x, y)) continue;
             keys[off] = tbase + (uint32_t)(y * c.gx + x);
             vals[off] = i;
             off++;
@@ -207,16 +223,16 @@ bool bin_fits_fast_path(uint32_t max_count) { return max_count <= (uint32_t)BIN_
 size_t bin_scratch_bytes(const DevCfg &c, int64_t D, bool fast) {
     const size_t n = (size_t)c.V * c.P;
     if (fast) return align256((size_t)(D > 0 ? D : 1) * 8);
-    // depth_keys[n] | order[n] | offsets[n] | keys_in[D] | keys_out[D] | vals_in[D] | cub temp
-    return 2 * align256(n * 8) + align256(n * 4) + 3 * align256((size_t)D * 4) + cub_temp_bytes(c, (int64_t)n, D);
+    // depth_keys[n] | order[n] | cnt[n] | offsets[n] | keys_in[D] | keys_out[D] | vals_in[D] | cub temp
+    return 2 * align256(n * 8) + 2 * align256(n * 4) + 3 * align256((size_t)D * 4) + cub_temp_bytes(c, (int64_t)n, D);
 }
 
-int bin_emit_fast(const DevCfg &c, int64_t D, const float4 *rec2, const ushort4 *rects, const uint32_t *offsets,
-                  uint32_t *cursor, void *scratch, cudaStream_t st) {
+int bin_emit_fast(const DevCfg &c, int64_t D, const float4 *rec0, const float4 *rec1, const float4 *rec2,
+                  const ushort4 *rects, const uint32_t *offsets, uint32_t *cursor, void *scratch, cudaStream_t st) {
     if (D <= 0) return GS_OK;
     GS_CUDA_OK(cudaMemsetAsync(cursor, 0, bin_counter_bytes(c), st));
     const size_t n = (size_t)c.V * c.P;
-    k_emit_buckets<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c, rec2, rects, offsets, cursor,
+    k_emit_buckets<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c, rec0, rec1, rec2, rects, offsets, cursor,
                                                                  static_cast<uint64_t *>(scratch));
     GS_CUDA_OK(cudaGetLastError());
     return GS_OK;
@@ -232,8 +248,9 @@ int bin_sort_fast(const DevCfg &c, uint32_t max_count, const uint32_t *tile_star
     return launch_tile_sort<BIN_SMEM_CAP / TS_THREADS>(nvt, tile_n, tile_start, bucket, point_list, ranges, st);
 }
 
-int bin_sort_fallback(const DevCfg &c, int64_t D, const float4 *rec2, const ushort4 *rects, void *scratch,
-                      size_t scratch_bytes, uint32_t *point_list, uint2 *ranges, cudaStream_t st) {
+int bin_sort_fallback(const DevCfg &c, int64_t D, const float4 *rec0, const float4 *rec1, const float4 *rec2,
+                      const ushort4 *rects, void *scratch, size_t scratch_bytes, uint32_t *point_list, uint2 *ranges,
+                      cudaStream_t st) {
     GS_CUDA_OK(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)c.V * c.ntiles, st));
     if (D == 0) return GS_OK;
     const size_t n = (size_t)c.V * c.P;
@@ -245,6 +262,7 @@ int bin_sort_fallback(const DevCfg &c, int64_t D, const float4 *rec2, const usho
     };
     uint64_t *depth_keys = reinterpret_cast<uint64_t *>(take(n * 8));
     uint64_t *order = reinterpret_cast<uint64_t *>(take(n * 8));
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(take(n * 4));
     uint32_t *offsets = reinterpret_cast<uint32_t *>(take(n * 4));
     uint32_t *keys_in = reinterpret_cast<uint32_t *>(take((size_t)D * 4));
     uint32_t *keys_out = reinterpret_cast<uint32_t *>(take((size_t)D * 4));
@@ -252,12 +270,12 @@ int bin_sort_fallback(const DevCfg &c, int64_t D, const float4 *rec2, const usho
     size_t temp_bytes = scratch_bytes - (size_t)(p - static_cast<unsigned char *>(scratch));
     const unsigned blocks = (unsigned)((n + 255) / 256);
 
-    k_depth_keys<<<blocks, 256, 0, st>>>(n, rec2, rects, depth_keys);
+    k_depth_keys<<<blocks, 256, 0, st>>>(n, rec0, rec1, rec2, rects, depth_keys, cnt);
     GS_CUDA_OK(cudaGetLastError());
     GS_CUDA_OK(cub::DeviceRadixSort::SortKeys(p, temp_bytes, depth_keys, order, (int)n, 32, 64, st));
-    auto it = thrust::make_transform_iterator((const uint64_t *)order, TilesInOrder{rects});
+    auto it = thrust::make_transform_iterator((const uint64_t *)order, TilesInOrder{cnt});
     GS_CUDA_OK(cub::DeviceScan::InclusiveSum(p, temp_bytes, it, offsets, (int)n, st));
-    k_emit_ordered<<<blocks, 256, 0, st>>>(c, order, rects, offsets, keys_in, vals_in);
+    k_emit_ordered<<<blocks, 256, 0, st>>>(c, order, rec0, rec1, rec2, rects, cnt, offsets, keys_in, vals_in);
     GS_CUDA_OK(cudaGetLastError());
     GS_CUDA_OK(cub::DeviceRadixSort::SortPairs(p, temp_bytes, keys_in, keys_out, vals_in, point_list, (int)D, 0,
                                                tile_bits(c), st));

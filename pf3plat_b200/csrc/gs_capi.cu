@@ -328,8 +328,11 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     if (rc != GS_OK) return fail(rc);
     {
         StageTimer t(ctx, GS_STAGE_BIN_EMIT, st);
-        if (fast) rc = bin_emit_fast(c, D, s->rec2, rects, sub_offsets, cursor, ctx->sort.p, st);
-        else rc = bin_sort_fallback(c, D, s->rec2, rects, ctx->sort.p, ctx->sort.bytes, s->point_list, s->ranges, st);
+        if (fast)
+            rc = bin_emit_fast(c, D, s->rec0, s->rec1, s->rec2, rects, sub_offsets, cursor, ctx->sort.p, st);
+        else
+            rc = bin_sort_fallback(c, D, s->rec0, s->rec1, s->rec2, rects, ctx->sort.p, ctx->sort.bytes, s->point_list,
+                                   s->ranges, st);
         if (rc != GS_OK) return fail(rc);
     }
     if (fast) {

@@ -4,7 +4,8 @@
 // V*P entries each, written by preprocess and gathered by the compositors with 16-byte loads:
 //   rec0 = (x_pix, y_pix, -0.5*log2e*conic_a, -log2e*conic_b)
 //   rec1 = (-0.5*log2e*conic_c, opacity, r, g)
-//   rec2 = (b, z_cam, hx, hy)         hx,hy = half extents of the alpha >= 1/255 ellipse's bounding box
+//   rec2 = (b, z_cam, reach2, 0)      reach2 = -(log2(255*opacity) + margin): a pixel can receive the Gaussian
+//                                     only where log2 G >= reach2 (see gs_box_reaches)
 // The conic is stored pre-scaled so that the compositors get log2(G) = power*log2(e) with five FP ops and feed
 // it straight to ex2.approx (gs_power2 / gs_ex2 below; forward and backward share them bit for bit).
 // plus meta[V*P] (uint8: bits 0-2 = SH clamp flags, bit 3 = visible).
@@ -69,12 +70,13 @@ int bin_tile_scan(const DevCfg &c, const uint32_t *counters, uint32_t *offsets, 
                   uint32_t *info, cudaStream_t st);
 bool bin_fits_fast_path(uint32_t max_count);
 size_t bin_scratch_bytes(const DevCfg &c, int64_t D, bool fast);
-int bin_emit_fast(const DevCfg &c, int64_t D, const float4 *rec2, const ushort4 *rects, const uint32_t *offsets,
-                  uint32_t *cursor, void *scratch, cudaStream_t st);
+int bin_emit_fast(const DevCfg &c, int64_t D, const float4 *rec0, const float4 *rec1, const float4 *rec2,
+                  const ushort4 *rects, const uint32_t *offsets, uint32_t *cursor, void *scratch, cudaStream_t st);
 int bin_sort_fast(const DevCfg &c, uint32_t max_count, const uint32_t *tile_start, const uint32_t *tile_n,
                   const void *scratch, uint32_t *point_list, uint2 *ranges, cudaStream_t st);
-int bin_sort_fallback(const DevCfg &c, int64_t D, const float4 *rec2, const ushort4 *rects, void *scratch,
-                      size_t scratch_bytes, uint32_t *point_list, uint2 *ranges, cudaStream_t st);
+int bin_sort_fallback(const DevCfg &c, int64_t D, const float4 *rec0, const float4 *rec1, const float4 *rec2,
+                      const ushort4 *rects, void *scratch, size_t scratch_bytes, uint32_t *point_list, uint2 *ranges,
+                      cudaStream_t st);
 
 int launch_composite_fwd(const DevCfg &c, const GsSaved &s, float *color, float *depth, cudaStream_t st);
 int launch_composite_bwd(const DevCfg &c, const GsSaved &s, const float *dL_dcolor, const float *dL_ddepth,
@@ -204,6 +206,29 @@ __device__ __forceinline__ float gs_power2(float hA, float nB, float hC, float d
     const float t2 = __fmul_rn(hC, dy);
     return __fmaf_rn(dx, t1, __fmul_rn(dy, t2));
 }
+// Can the Gaussian reach (alpha >= 1/255) ANY point of the axis-aligned box [x0,x1] x [y0,y1] (pixel coordinates)?
+// Exact for the continuous box, hence conservative for the pixel centres inside it: the maximum of the concave
+// quadratic log2 G over the box is 0 if the centre is inside, else it lies on one of the two edges facing the
+// centre, where it is a clamped 1-D maximisation.  Used for tile binning (16x16 boxes) and for the compositors'
+// per-warp culling (8x4 boxes); reach2 carries the rounding margin.
+__device__ __forceinline__ bool gs_box_reaches(float cx, float cy, float hA, float nB, float hC, float reach2,
+                                               float x0, float x1, float y0, float y1) {
+    const float bx0 = x0 - cx, bx1 = x1 - cx, by0 = y0 - cy, by1 = y1 - cy;
+    const float xe = fminf(fmaxf(0.0f, bx0), bx1), ye = fminf(fmaxf(0.0f, by0), by1);  // box point nearest the centre
+    // edge x = xe: best y solves d/dy = nB*xe + 2*hC*y = 0 ; edge y = ye: best x solves nB*ye + 2*hA*x = 0
+    const float yb = fminf(fmaxf(__fdividef(-nB * xe, 2.0f * hC), by0), by1);
+    const float xb = fminf(fmaxf(__fdividef(-nB * ye, 2.0f * hA), bx0), bx1);
+    const float p1 = gs_power2(hA, nB, hC, xe, yb), p2 = gs_power2(hA, nB, hC, xb, ye);
+    return fmaxf(p1, p2) >= reach2;
+}
+
+// The binning predicate shared by k_preprocess (counting) and k_emit_buckets (emission): does the Gaussian with
+// records (r0, r1, r2) reach tile (tx, ty)?  Both kernels evaluate it on the same stored values.
+__device__ __forceinline__ bool gs_tile_reached(float4 r0, float4 r1, float4 r2, int tx, int ty) {
+    const float x0 = (float)(tx * GS_TILE), y0 = (float)(ty * GS_TILE);
+    return gs_box_reaches(r0.x, r0.y, r0.z, r0.w, r1.x, r2.z, x0, x0 + (float)(GS_TILE - 1), y0, y0 + (float)(GS_TILE - 1));
+}
+
 __device__ __forceinline__ float gs_ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

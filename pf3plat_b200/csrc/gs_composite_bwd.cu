@@ -102,7 +102,7 @@ k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
                 const uint2 *__restrict__ ranges, const float *__restrict__ final_T,
                 const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dcolor,
                 const float *__restrict__ dL_ddepth, float *__restrict__ acc) {
-    __shared__ float4 s_box[CB_BATCH];     // (x, y, hx, hy) per Gaussian: read by lane k for Gaussian k
+    __shared__ float4 s_cull[CB_BATCH];    // (hC, reach2, -, -): with s_rec[.][0] all the exact box test needs
     __shared__ float4 s_rec[CB_BATCH][3];  // rec0 | rec1 | rec2, read as warp-wide broadcasts
     __shared__ uint32_t sid[CB_BATCH];
     __shared__ uint32_t s_max[CB_THREADS / 32];
@@ -115,9 +115,9 @@ k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
     const int px = bx + (lane & 7), py = by + (lane >> 3);
     const bool inside = px < c.W && py < c.H;
     const float pxf = (float)px, pyf = (float)py;
-    const float bcx = (float)bx + 3.5f, bcy = (float)by + 1.5f;  // block centre (half size 3.5 x 1.5)
+    const float bx0 = (float)bx, bx1 = (float)(bx + 7), by0 = (float)by, by1 = (float)(by + 3);
     const float half_w = 0.5f * (float)c.W, half_h = 0.5f * (float)c.H;
-    const uint32_t box_addr = smem_u32(&s_box[0]), rec_addr = smem_u32(&s_rec[0][0]);
+    const uint32_t cull_addr = smem_u32(&s_cull[0]), rec_addr = smem_u32(&s_rec[0][0]);
 
     const uint2 range = ranges[(size_t)v * c.ntiles + tile];
     const size_t rbase = (size_t)v * c.P;
@@ -163,7 +163,7 @@ k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
             const size_t r = rbase + id;
             const float4 q0 = rec0[r], q1 = rec1[r], q2 = rec2[r];
             sid[tid] = id;
-            s_box[tid] = make_float4(q0.x, q0.y, q2.z, q2.w);
+            s_cull[tid] = make_float4(q1.x, q2.z, 0.f, 0.f);
             s_rec[tid][0] = q0;
             s_rec[tid][1] = q1;
             s_rec[tid][2] = q2;
@@ -174,8 +174,9 @@ k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
             const uint32_t j = (uint32_t)chunk + lane;
             bool hit = false;
             if (j < nb && lo + j < warp_last) {
-                const float4 bb = lds128(box_addr + j * 16u);
-                hit = (fabsf(bb.x - bcx) <= bb.z + 3.5f) && (fabsf(bb.y - bcy) <= bb.w + 1.5f);
+                const float4 g0 = lds128(rec_addr + j * 48u);
+                const float2 g1 = lds64(cull_addr + j * 16u);
+                hit = gs_box_reaches(g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, bx0, bx1, by0, by1);
             }
             uint32_t mask = __ballot_sync(0xffffffffu, hit);
             while (mask) {

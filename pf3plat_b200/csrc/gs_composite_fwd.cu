@@ -23,9 +23,9 @@ namespace {
 constexpr int CF_THREADS = 256;
 constexpr int CF_BATCH = 256;
 
-// Shared-memory staging of one batch: per Gaussian a 16-byte cull box and a 48-byte evaluation record.
+// Shared-memory staging of one batch: per Gaussian a 16-byte cull record and a 48-byte evaluation record.
 struct CfBatch {
-    float4 box[CF_BATCH];      // (x, y, hx, hy): read by lane k for Gaussian k (conflict-free LDS.128)
+    float4 cull[CF_BATCH];     // (hC, reach2, -, -): with rec[.][0] all the exact box test needs; lane k reads entry k
     float4 rec[CF_BATCH][3];   // rec0 | rec1 | rec2 of gs_common.cuh, read as warp-wide broadcasts
 };
 
@@ -45,12 +45,11 @@ k_composite_fwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
     const int px = bx + (lane & 7), py = by + (lane >> 3);
     const bool inside = px < c.W && py < c.H;
     const float pxf = (float)px, pyf = (float)py;
-    // block centre and half size: the cull test is |x - cx| <= hx + 3.5 && |y - cy| <= hy + 1.5
-    const float bcx = (float)bx + 3.5f, bcy = (float)by + 1.5f;
+    const float bx0 = (float)bx, bx1 = (float)(bx + 7), by0 = (float)by, by1 = (float)(by + 3);
 
     const uint2 range = ranges[(size_t)v * c.ntiles + tile];
     const size_t rbase = (size_t)v * c.P;
-    const uint32_t box_addr = smem_u32(&sm.box[0]), rec_addr = smem_u32(&sm.rec[0][0]);
+    const uint32_t cull_addr = smem_u32(&sm.cull[0]), rec_addr = smem_u32(&sm.rec[0][0]);
 
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dz = 0.f;
     uint32_t last = 0;
@@ -63,7 +62,7 @@ k_composite_fwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
         if ((uint32_t)tid < nb) {
             const size_t r = rbase + point_list[base + tid];
             const float4 q0 = rec0[r], q1 = rec1[r], q2 = rec2[r];
-            sm.box[tid] = make_float4(q0.x, q0.y, q2.z, q2.w);
+            sm.cull[tid] = make_float4(q1.x, q2.z, 0.f, 0.f);
             sm.rec[tid][0] = q0;
             sm.rec[tid][1] = q1;
             sm.rec[tid][2] = q2;
@@ -75,8 +74,10 @@ k_composite_fwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
             const uint32_t j = chunk + lane;
             bool hit = false;
             if (j < nb) {
-                const float4 bb = lds128(box_addr + j * 16u);
-                hit = (fabsf(bb.x - bcx) <= bb.z + 3.5f) && (fabsf(bb.y - bcy) <= bb.w + 1.5f);
+                // exact: does the alpha >= 1/255 ellipse reach this warp's 8x4 block?
+                const float4 g0 = lds128(rec_addr + j * 48u);
+                const float2 g1 = lds64(cull_addr + j * 16u);
+                hit = gs_box_reaches(g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, bx0, bx1, by0, by1);
             }
             uint32_t mask = __ballot_sync(0xffffffffu, hit);
             const uint32_t chunk_addr = rec_addr + chunk * 48u;

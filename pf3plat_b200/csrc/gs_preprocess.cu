@@ -55,7 +55,7 @@ __device__ __forceinline__ float3 eval_sh(int deg, const float *sh /* [M][3] for
 struct Splat {
     float4 r0, r1, r2;
     int32_t radius;
-    uint32_t tiles, meta;
+    uint32_t meta;
     ushort4 rect;
 };
 
@@ -65,7 +65,6 @@ template <bool HAS_SH>
 __device__ __forceinline__ void project_splat(const DevCfg &c, const ViewCam &cam, float3 mean, const float *c6,
                                               float opac, const float *sh, const float *rgb_in, Splat &out) {
     out.radius = 0;
-    out.tiles = 0;
     out.meta = 0;
     out.rect = make_ushort4(0, 0, 0, 0);
     const float s = cam.scale, s2 = s * s;
@@ -108,15 +107,19 @@ __device__ __forceinline__ void project_splat(const DevCfg &c, const ViewCam &ca
     } else {
         rgb = make_float3(rgb_in[0], rgb_in[1], rgb_in[2]);
     }
-    // Tight binning.  A pixel can only receive this Gaussian if alpha = o*exp(-q/2) >= 1/255, i.e. inside the
-    // ellipse q = d^T Q d <= tau = 2 ln(255 o).  Its bounding box has half extents sqrt(tau * Qinv_ii); tiles
-    // outside it (or outside upstream's square) cannot change any pixel, so they are not binned.  tau carries a
-    // margin for the fp32 rounding of q in the compositor (grows with the reach of the footprint), and the
-    // determinant is taken in fp64 from the fp32 conic actually used by the compositor.
-    float hx = 0.f, hy = 0.f;
+    // Tight binning.  A pixel can only receive this Gaussian if alpha = o*G >= 1/255, i.e. log2 G >= -log2(255 o):
+    // inside the ellipse q = d^T Q d <= tau = 2 ln(255 o).  Candidate tiles are those of the ellipse's bounding box
+    // (half extents sqrt(tau * Qinv_ii)) intersected with upstream's 3-sigma square; k_preprocess / k_emit_buckets then
+    // keep a candidate only if the ellipse really reaches it (gs_box_reaches).  Tiles dropped this way cannot change
+    // any pixel.  The threshold carries a margin for the fp32 rounding of q in the compositor (it grows with the
+    // reach of the footprint), and the bounding box takes its determinant in fp64 from the stored fp32 conic.
     const float reach = rad + (float)GS_TILE;
-    const float tau = 2.0f * logf(255.0f * opac) + 1e-3f + 4e-6f * reach * reach;
+    const float margin = 1e-3f + 4e-6f * reach * reach;              // in units of tau
+    const float tau = 2.0f * logf(255.0f * opac) + margin;
+    const float hA = (-0.5f * GS_LOG2E) * A, nB = -GS_LOG2E * B, hC = (-0.5f * GS_LOG2E) * C;
+    const float reach2 = -(0.5f * GS_LOG2E) * tau;                     // same threshold in log2-G units
     if (tau > 0.0f) {
+        float hx, hy;
         const double dq = (double)A * (double)C - (double)B * (double)B;
         if (dq > 0.0) {
             hx = (float)sqrt((double)tau * (double)C / dq) * 1.0001f + 1e-3f;
@@ -130,14 +133,12 @@ __device__ __forceinline__ void project_splat(const DevCfg &c, const ViewCam &ca
         const int tx0 = max(rminx, (int)fmaxf(fx0, 0.0f)), ty0 = max(rminy, (int)fmaxf(fy0, 0.0f));
         const int tx1 = fx1 < 0.0f ? 0 : min(rmaxx, (int)fminf(fx1, 65534.0f) + 1);
         const int ty1 = fy1 < 0.0f ? 0 : min(rmaxy, (int)fminf(fy1, 65534.0f) + 1);
-        if (tx1 > tx0 && ty1 > ty0) {
-            out.tiles = (uint32_t)(tx1 - tx0) * (uint32_t)(ty1 - ty0);
+        if (tx1 > tx0 && ty1 > ty0)
             out.rect = make_ushort4((unsigned short)tx0, (unsigned short)ty0, (unsigned short)tx1, (unsigned short)ty1);
-        }
     }
-    out.r0 = make_float4(px, py, (-0.5f * GS_LOG2E) * A, -GS_LOG2E * B);
-    out.r1 = make_float4((-0.5f * GS_LOG2E) * C, opac, rgb.x, rgb.y);
-    out.r2 = make_float4(rgb.z, pv.z, hx, hy);
+    out.r0 = make_float4(px, py, hA, nB);
+    out.r1 = make_float4(hC, opac, rgb.x, rgb.y);
+    out.r2 = make_float4(rgb.z, pv.z, reach2, 0.0f);
 }
 
 template <bool HAS_SH>
@@ -219,8 +220,9 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
             // sub-counter i % BIN_SUB, one counter per 32-byte sector -- see gs_binning.cu)
             for (int ty = sp.rect.y; ty < sp.rect.w; ty++)
                 for (int tx = sp.rect.x; tx < sp.rect.z; tx++)
-                    atomicAdd(&tile_counts[(((size_t)v * c.ntiles + ty * c.gx + tx) * BIN_SUB + (i & (BIN_SUB - 1))) * BIN_PAD],
-                              1u);
+                    if (gs_tile_reached(sp.r0, sp.r1, sp.r2, tx, ty))
+                        atomicAdd(&tile_counts[(((size_t)v * c.ntiles + ty * c.gx + tx) * BIN_SUB + (i & (BIN_SUB - 1))) * BIN_PAD],
+                                  1u);
             meta[o] = (uint8_t)sp.meta;
         }
     }
