@@ -15,7 +15,10 @@
 // Tried and dropped: fusing the per-tile merge sort (k_tile_sort, latency-bound, 22 % issue) into this kernel's
 // prologue so that one CTA's sort latency hides behind other CTAs' compositing.  Measured on C2: 0.663 ms fused vs
 // 0.303 + 0.340 ms separate; on C4 12.6 vs 9.1 ms (the sort's 63-125 registers cut the compositor's occupancy, and
-// CTAs of a wave run their phases in lock-step, so little overlap materialises).
+// CTAs of a wave run their phases in lock-step, so little overlap materialises).  Also tried: a two-stage software
+// pipeline over groups of views (k_tile_sort of group g+1 on a side stream under the compositing of group g):
+// 1.21 ms per C2 forward vs 1.01 ms serial -- the co-resident sort CTAs take registers/shared memory from the
+// compositor without filling its idle issue slots.
 #include "gs_common.cuh"
 
 namespace {
