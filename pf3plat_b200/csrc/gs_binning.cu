@@ -93,17 +93,31 @@ __global__ void k_emit_buckets(const DevCfg c, const float4 *__restrict__ rec0, 
     const uint64_t key = ((uint64_t)__float_as_uint(q2.y) << 32) | i;
     const uint32_t tbase = v * (uint32_t)c.ntiles;
     const uint32_t sub = i & (BIN_SUB - 1);
-    for (int y = r.y; y < r.w; y++)
-        for (int x = r.x; x < r.z; x++) {
-            if (!gs_tile_reached(q0, q1, q2, x, y)) continue;  // same predicate as the count in k_preprocess
-            const size_t slot = (size_t)(tbase + (uint32_t)(y * c.gx + x)) * BIN_SUB + sub;
-            const uint32_t pos = atomicAdd(&cursor[slot * BIN_PAD], 1u);
-            bucket[(size_t)offsets[slot] + pos] = key;
+    // The cursor atomics return values and the stores depend on them: handle the candidate tiles four at a time so
+    // that several round trips to L2 are in flight per thread (the kernel is latency-bound: 16 % of issue slots busy).
+    constexpr int BATCH = 4;
+    const int w = r.z - r.x, nt = w * (r.w - r.y);
+    for (int t0 = 0; t0 < nt; t0 += BATCH) {
+        size_t slot[BATCH];
+        uint32_t pos[BATCH];
+        bool ok[BATCH];
+#pragma unroll
+        for (int k = 0; k < BATCH; k++) {
+            const int t = t0 + k, ty = r.y + t / w, tx = r.x + t - (t / w) * w;
+            ok[k] = t < nt && gs_tile_reached(q0, q1, q2, tx, ty);  // same predicate as the count in k_preprocess
+            slot[k] = (size_t)(tbase + (uint32_t)(ty * c.gx + tx)) * BIN_SUB + sub;
         }
+#pragma unroll
+        for (int k = 0; k < BATCH; k++)
+            if (ok[k]) pos[k] = atomicAdd(&cursor[slot[k] * BIN_PAD], 1u);
+#pragma unroll
+        for (int k = 0; k < BATCH; k++)
+            if (ok[k]) bucket[(size_t)offsets[slot[k]] + pos[k]] = key;
+    }
 }
 
-template <int MAX_ITEMS>
-__global__ void __launch_bounds__(TS_THREADS)
+template <int THREADS, int MAX_ITEMS>
+__global__ void __launch_bounds__(THREADS)
 k_tile_sort(const uint32_t *__restrict__ tile_n, const uint32_t *__restrict__ tile_start,
             const uint64_t *__restrict__ bucket, uint32_t *__restrict__ point_list, uint2 *__restrict__ ranges) {
     extern __shared__ __align__(16) unsigned char ts_smem[];
@@ -111,19 +125,29 @@ k_tile_sort(const uint32_t *__restrict__ tile_n, const uint32_t *__restrict__ ti
     const uint32_t n = tile_n[vt], off = tile_start[vt];
     if (threadIdx.x == 0) ranges[vt] = make_uint2(off, off + n);
     if (n == 0) return;
-    const uint64_t *src = bucket + off;
-    uint32_t *dst = point_list + off;
-    sort_bucket_dispatch<MAX_ITEMS>(src, dst, n, ts_smem);
+    sort_bucket_dispatch<THREADS, MAX_ITEMS>(bucket + off, point_list + off, n, ts_smem);
 }
 
-template <int MAX_ITEMS>
+template <int THREADS, int MAX_ITEMS>
 int launch_tile_sort(int nvt, const uint32_t *counts, const uint32_t *offsets, const uint64_t *bucket,
                      uint32_t *point_list, uint2 *ranges, cudaStream_t st) {
-    const size_t smem = tile_sort_smem_bytes<MAX_ITEMS>();
-    GS_CUDA_OK(cudaFuncSetAttribute(k_tile_sort<MAX_ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_tile_sort<MAX_ITEMS><<<nvt, TS_THREADS, smem, st>>>(counts, offsets, bucket, point_list, ranges);
+    const size_t smem = tile_sort_smem_bytes<THREADS, MAX_ITEMS>();
+    GS_CUDA_OK(cudaFuncSetAttribute(k_tile_sort<THREADS, MAX_ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tile_sort<THREADS, MAX_ITEMS><<<nvt, THREADS, smem, st>>>(counts, offsets, bucket, point_list, ranges);
     GS_CUDA_OK(cudaGetLastError());
     return GS_OK;
+}
+
+// Capacity ladder of the per-tile sort: the smallest (threads x keys-per-thread) configuration that holds the
+// longest list of the call.  More threads with fewer keys each shorten the serial part of every merge round.
+template <int THREADS>
+int dispatch_tile_sort(uint32_t max_count, int nvt, const uint32_t *tile_n, const uint32_t *tile_start,
+                       const uint64_t *bucket, uint32_t *point_list, uint2 *ranges, cudaStream_t st) {
+    constexpr int CAP_ITEMS = BIN_SMEM_CAP / THREADS;
+    if (max_count <= THREADS * (CAP_ITEMS / 8)) return launch_tile_sort<THREADS, CAP_ITEMS / 8>(nvt, tile_n, tile_start, bucket, point_list, ranges, st);
+    if (max_count <= THREADS * (CAP_ITEMS / 4)) return launch_tile_sort<THREADS, CAP_ITEMS / 4>(nvt, tile_n, tile_start, bucket, point_list, ranges, st);
+    if (max_count <= THREADS * (CAP_ITEMS / 2)) return launch_tile_sort<THREADS, CAP_ITEMS / 2>(nvt, tile_n, tile_start, bucket, point_list, ranges, st);
+    return launch_tile_sort<THREADS, CAP_ITEMS>(nvt, tile_n, tile_start, bucket, point_list, ranges, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -242,10 +266,12 @@ int bin_sort_fast(const DevCfg &c, uint32_t max_count, const uint32_t *tile_star
                   const void *scratch, uint32_t *point_list, uint2 *ranges, cudaStream_t st) {
     const int nvt = c.V * c.ntiles;
     const uint64_t *bucket = static_cast<const uint64_t *>(scratch);
-    if (max_count <= TS_THREADS * 2) return launch_tile_sort<2>(nvt, tile_n, tile_start, bucket, point_list, ranges, st);
-    if (max_count <= TS_THREADS * 8) return launch_tile_sort<8>(nvt, tile_n, tile_start, bucket, point_list, ranges, st);
-    if (max_count <= TS_THREADS * 16) return launch_tile_sort<16>(nvt, tile_n, tile_start, bucket, point_list, ranges, st);
-    return launch_tile_sort<BIN_SMEM_CAP / TS_THREADS>(nvt, tile_n, tile_start, bucket, point_list, ranges, st);
+    // The merge sort is latency-bound: every round is a binary search plus a serial merge of ITEMS keys per thread.
+    // Fewer keys per thread (more threads per tile) shorten the serial part -- measured on C2 (lists of ~3.3k):
+    // 256 x 16: 0.318 ms, 512 x 8: 0.259 ms, 1024 x 4: 0.245 ms -- so long lists get 1024 threads.
+    if (max_count > 2048) return dispatch_tile_sort<1024>(max_count, nvt, tile_n, tile_start, bucket, point_list, ranges, st);
+    if (max_count > 1024) return dispatch_tile_sort<512>(max_count, nvt, tile_n, tile_start, bucket, point_list, ranges, st);
+    return dispatch_tile_sort<256>(max_count, nvt, tile_n, tile_start, bucket, point_list, ranges, st);
 }
 
 int bin_sort_fallback(const DevCfg &c, int64_t D, const float4 *rec0, const float4 *rec1, const float4 *rec2,

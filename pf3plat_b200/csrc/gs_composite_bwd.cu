@@ -56,42 +56,43 @@ __device__ __forceinline__ bool pixel_grad(PixState &ps, bool live, uint32_t rec
     const float alpha = fminf(GS_ALPHA_MAX, q1.y * G);
     // one divergent region: the test above is evaluated by all lanes unconditionally
     if (!(live && p2 <= 0.0f && alpha >= GS_ALPHA_MIN)) return false;
-    const float2 q2 = lds64(rec_addr + 32u);
+    const float2 q2 = lds64(rec_addr + 32u);  // (b, z)
     // one approximate reciprocal (MUFU.RCP, <= 1 ulp) serves both divisions by (1 - alpha); the IEEE divisions
     // upstream uses cost ~10 instructions each and the 1e-3 gradient tolerance does not need them
     const float inv_1ma = gs_rcp(1.0f - alpha);
-    ps.T = ps.T * inv_1ma;
+    ps.T *= inv_1ma;
     const float w = alpha * ps.T;
-    const float col[3] = {q1.z, q1.w, q2.x};  // q2 = (b, z)
+    const float keep = 1.0f - ps.last_alpha;
+    const float col[3] = {q1.z, q1.w, q2.x};
     float dL_dalpha = 0.f;
 #pragma unroll
     for (int ch = 0; ch < 3; ch++) {
-        ps.accum[ch] = ps.last_alpha * ps.last_color[ch] + (1.0f - ps.last_alpha) * ps.accum[ch];
+        ps.accum[ch] = fmaf(ps.last_alpha, ps.last_color[ch], keep * ps.accum[ch]);
         ps.last_color[ch] = col[ch];
-        dL_dalpha += (col[ch] - ps.accum[ch]) * ps.dLp[ch];
+        dL_dalpha = fmaf(col[ch] - ps.accum[ch], ps.dLp[ch], dL_dalpha);
         g[ch] = w * ps.dLp[ch];
     }
     if (DEPTH) {
-        ps.accum_d = ps.last_alpha * ps.last_d + (1.0f - ps.last_alpha) * ps.accum_d;
+        ps.accum_d = fmaf(ps.last_alpha, ps.last_d, keep * ps.accum_d);
         ps.last_d = q2.y;
-        dL_dalpha += (q2.y - ps.accum_d) * ps.dLd;
+        dL_dalpha = fmaf(q2.y - ps.accum_d, ps.dLd, dL_dalpha);
         g[9] = w * ps.dLd;
     }
-    dL_dalpha *= ps.T;
     ps.last_alpha = alpha;
-    dL_dalpha -= ps.T_final * inv_1ma * ps.bg_dot;
-    const float dL_dG = q1.y * dL_dalpha;  // straight through the 0.99 clamp
-    // true conic from the pre-scaled record: A = hA * (-2/log2e), B = nB * (-1/log2e)
-    const float A = q0.z * (-2.0f / GS_LOG2E), B = q0.w * (-1.0f / GS_LOG2E), Cc = q1.x * (-2.0f / GS_LOG2E);
-    const float gdx = G * dx, gdy = G * dy;
-    const float dG_ddelx = -gdx * A - gdy * B;
-    const float dG_ddely = -gdy * Cc - gdx * B;
-    g[3] = dL_dG * dG_ddelx * half_w;
-    g[4] = dL_dG * dG_ddely * half_h;
-    g[5] = -0.5f * gdx * dx * dL_dG;
-    g[6] = -0.5f * gdx * dy * dL_dG;
-    g[7] = -0.5f * gdy * dy * dL_dG;
-    g[8] = G * dL_dalpha;
+    dL_dalpha = fmaf(dL_dalpha, ps.T, -(ps.T_final * inv_1ma) * ps.bg_dot);
+    // With s = G dL/dalpha (the opacity gradient; dL/dG = o dL/dalpha passes straight through the 0.99 clamp) and
+    // m = -0.5 o s, written in the pre-scaled conic (A = -2 ln2 hA, B = -ln2 nB, C = -2 ln2 hC):
+    //   dL/dconic = m (dx^2, dx dy, dy^2)
+    //   dL/dmean2D = m (-2 ln2) (W/2 (2 hA dx + nB dy), H/2 (2 hC dy + nB dx))
+    const float sgrad = dL_dalpha * G;
+    const float m = (-0.5f * q1.y) * sgrad;
+    const float mdx = m * dx, mdy = m * dy;
+    g[3] = (m * (-2.0f * 0.6931471805599453f * half_w)) * fmaf(q0.z + q0.z, dx, q0.w * dy);
+    g[4] = (m * (-2.0f * 0.6931471805599453f * half_h)) * fmaf(q1.x + q1.x, dy, q0.w * dx);
+    g[5] = mdx * dx;
+    g[6] = mdx * dy;
+    g[7] = mdy * dy;
+    g[8] = sgrad;
     return true;
 }
 

@@ -5,20 +5,18 @@
 
 #include "gs_common.cuh"
 
-#define TS_THREADS 256
-
-// Bytes of shared memory sort_bucket_merge<ITEMS> needs.
-template <int ITEMS>
+// Bytes of shared memory sort_bucket_merge<THREADS, ITEMS> needs.
+template <int THREADS, int ITEMS>
 constexpr size_t tile_sort_smem_bytes() {
-    return sizeof(typename cub::BlockMergeSort<uint64_t, TS_THREADS, ITEMS>::TempStorage);
+    return sizeof(typename cub::BlockMergeSort<uint64_t, THREADS, ITEMS>::TempStorage);
 }
 
 // 64-bit merge sort of one bucket: (depth_bits << 32 | index) is a total order, so the arbitrary arrival order of
-// the bucket does not matter.  All TS_THREADS threads of the CTA call it; dst receives the indices in order.
-template <int ITEMS>
+// the bucket does not matter.  All THREADS threads of the CTA call it; dst receives the indices in order.
+template <int THREADS, int ITEMS>
 __device__ __forceinline__ void sort_bucket_merge(const uint64_t *__restrict__ src, uint32_t *__restrict__ dst,
                                                   uint32_t n, void *smem) {
-    using Sort = cub::BlockMergeSort<uint64_t, TS_THREADS, ITEMS>;
+    using Sort = cub::BlockMergeSort<uint64_t, THREADS, ITEMS>;
     typename Sort::TempStorage &tmp = *reinterpret_cast<typename Sort::TempStorage *>(smem);
     uint64_t keys[ITEMS];
     const uint32_t base = threadIdx.x * ITEMS;
@@ -30,12 +28,13 @@ __device__ __forceinline__ void sort_bucket_merge(const uint64_t *__restrict__ s
         if (base + k < n) dst[base + k] = (uint32_t)keys[k];
 }
 
-// Sorts a bucket of n <= TS_THREADS * MAX_ITEMS keys with the cheapest instantiation that fits it.
-template <int MAX_ITEMS>
+// Sorts a bucket of n <= THREADS * MAX_ITEMS keys with the cheapest instantiation (ITEMS in MAX/8, MAX/2, MAX) that
+// fits it.
+template <int THREADS, int MAX_ITEMS>
 __device__ __forceinline__ void sort_bucket_dispatch(const uint64_t *__restrict__ src, uint32_t *__restrict__ dst,
                                                      uint32_t n, void *smem) {
-    if (n <= TS_THREADS * 2) sort_bucket_merge<2>(src, dst, n, smem);
-    else if (MAX_ITEMS >= 8 && n <= TS_THREADS * 8) sort_bucket_merge<(MAX_ITEMS >= 8 ? 8 : 2)>(src, dst, n, smem);
-    else if (MAX_ITEMS >= 16 && n <= TS_THREADS * 16) sort_bucket_merge<(MAX_ITEMS >= 16 ? 16 : 2)>(src, dst, n, smem);
-    else sort_bucket_merge<MAX_ITEMS>(src, dst, n, smem);
+    constexpr int LO = MAX_ITEMS >= 8 ? MAX_ITEMS / 8 : 1, MID = MAX_ITEMS >= 2 ? MAX_ITEMS / 2 : 1;
+    if (n <= (uint32_t)THREADS * LO) sort_bucket_merge<THREADS, LO>(src, dst, n, smem);
+    else if (n <= (uint32_t)THREADS * MID) sort_bucket_merge<THREADS, MID>(src, dst, n, smem);
+    else sort_bucket_merge<THREADS, MAX_ITEMS>(src, dst, n, smem);
 }
