@@ -1,0 +1,41 @@
+"""Small forward+backward over every code path (SH / colours, cov / scale-rot, depth, fast / fallback binning) for
+compute-sanitizer:  compute-sanitizer --tool memcheck python scripts/sanitize_small.py"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pf3plat_b200._capi import GS_TUNE_FORCE_RADIX_BINNING  # noqa: E402
+from pf3plat_b200.cameras import make_view_batch  # noqa: E402
+from pf3plat_b200.rasterizer import BatchSettings, rasterize_batch  # noqa: E402
+from pf3plat_b200.synthetic import make_scene  # noqa: E402
+
+dev = torch.device("cuda:0")
+for (P, V, hw, tuning, depth, sr, sh) in [(3001, 3, (40, 56), 0, True, False, True),
+                                          (777, 1, (16, 16), GS_TUNE_FORCE_RADIX_BINNING, False, True, True),
+                                          (5000, 2, (33, 70), 0, True, False, False),
+                                          (130, 10, (64, 64), 0, False, False, True)]:
+    sc = make_scene(P, V, *hw, seed=P).to(dev)
+    vb = make_view_batch(sc.extrinsics, sc.intrinsics, sc.near, sc.far)
+    bs = BatchSettings(image_height=hw[0], image_width=hw[1], viewmatrix=vb.viewmatrix, projmatrix=vb.projmatrix,
+                       campos=vb.campos, bg=sc.background, sh_degree=4, tanfov=vb.tanfov, with_depth=depth, tuning=tuning)
+    means = sc.means[None].clone().requires_grad_(True)
+    opac = sc.opacities[None].clone().requires_grad_(True)
+    kw = {}
+    if sh:
+        kw["shs"] = sc.harmonics.permute(0, 2, 1).contiguous()[None].requires_grad_(True)
+    else:
+        kw["colors_precomp"] = sc.harmonics[:, :, 0][None].expand(V, P, 3).contiguous().requires_grad_(True)
+    if sr:
+        kw["scales"] = sc.scales[None].clone().requires_grad_(True)
+        kw["rotations"] = sc.rotations[None].clone().requires_grad_(True)
+    else:
+        c = sc.covariances
+        kw["cov3D_precomp"] = torch.stack([c[:, 0, 0], c[:, 0, 1], c[:, 0, 2], c[:, 1, 1], c[:, 1, 2], c[:, 2, 2]], -1)[None].requires_grad_(True)
+    out = rasterize_batch(bs, means, opac, **kw)
+    loss = out[0].square().mean() + (out[2].mean() if depth else 0)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert torch.isfinite(means.grad).all()
+    print("ok", P, V, hw, tuning, depth, sr, sh)

@@ -95,3 +95,47 @@ def test_orthographic_style_settings_with_tensor_tanfov():
     assert torch.equal(a, b_)
     vis = GaussianRasterizer(GaussianRasterizationSettings(tanfovx=0.58, tanfovy=0.58, **common)).markVisible(sc.means)
     assert vis.dtype == torch.bool and vis.all()      # every synthetic Gaussian sits at z >= 1.5
+
+
+def test_host_buffer_entry_matches_device_entry():
+    """gs_render_host (C ABI with HOST pointers: the e2e path of bench.py) against the torch-facing device path."""
+    import ctypes
+    from pf3plat_b200 import _capi, rasterizer
+    from pf3plat_b200.cameras import make_view_batch
+    from pf3plat_b200.rasterizer import BatchSettings, rasterize_batch
+    dev = torch.device("cuda:0")
+    P, V, hw = 20000, 3, (64, 80)
+    sc = make_scene(P, V, *hw, seed=9)
+    vb = make_view_batch(sc.extrinsics, sc.intrinsics, sc.near, sc.far)
+    c = sc.covariances
+    host = {"means3D": sc.means, "opacities": sc.opacities, "shs": sc.harmonics.permute(0, 2, 1).contiguous(),
+            "cov3D_precomp": torch.stack([c[:, 0, 0], c[:, 0, 1], c[:, 0, 2], c[:, 1, 1], c[:, 1, 2], c[:, 2, 2]], -1),
+            "viewmatrix": vb.viewmatrix, "projmatrix": vb.projmatrix, "campos": vb.campos, "bg": sc.background,
+            "tanfov": vb.tanfov}
+    host = {k: v.contiguous().float() for k, v in host.items()}          # pageable host memory is fine too
+    cfg = _capi.GsConfig()
+    cfg.P, cfg.S, cfg.V, cfg.M, cfg.sh_degree = P, 1, V, 25, 4
+    cfg.image_height, cfg.image_width, cfg.scale_modifier = hw[0], hw[1], 1.0
+    cfg.flags = _capi.GS_FLAG_DEPTH
+    for k in ("viewmatrix", "projmatrix", "campos", "bg", "tanfov"):
+        setattr(cfg, k, host[k].data_ptr())
+    gin = _capi.GsInputs(means3D=host["means3D"].data_ptr(), opacities=host["opacities"].data_ptr(),
+                         shs=host["shs"].data_ptr(), cov3D_precomp=host["cov3D_precomp"].data_ptr())
+    color = torch.empty(V, 3, *hw)
+    radii = torch.empty(V, P, dtype=torch.int32)
+    depth = torch.empty(V, *hw)
+    gout = _capi.GsOutputs(color=color.data_ptr(), radii=radii.data_ptr(), depth=depth.data_ptr())
+    ctx = rasterizer.current_context(dev)
+    _capi.check(_capi.lib().gs_render_host(ctx, ctypes.byref(cfg), ctypes.byref(gin), ctypes.byref(gout),
+                                           torch.cuda.current_stream(dev).cuda_stream))
+    d = {k: v.to(dev) for k, v in host.items()}
+    bs = BatchSettings(image_height=hw[0], image_width=hw[1], viewmatrix=d["viewmatrix"], projmatrix=d["projmatrix"],
+                       campos=d["campos"], bg=d["bg"], sh_degree=4, tanfov=d["tanfov"], with_depth=True)
+    c2, r2, d2 = rasterize_batch(bs, d["means3D"][None], d["opacities"][None], shs=d["shs"][None],
+                                 cov3D_precomp=d["cov3D_precomp"][None])
+    assert torch.equal(color, c2.cpu()) and torch.equal(radii, r2.cpu()) and torch.equal(depth, d2.cpu())
+    # invalid argument combinations come back as the reference op's exceptions, not crashes
+    bad = _capi.GsInputs(means3D=host["means3D"].data_ptr(), opacities=host["opacities"].data_ptr())
+    with pytest.raises(ValueError, match="SHs or precomputed colors"):
+        _capi.check(_capi.lib().gs_render_host(ctx, ctypes.byref(cfg), ctypes.byref(bad), ctypes.byref(gout),
+                                               torch.cuda.current_stream(dev).cuda_stream))
