@@ -269,8 +269,8 @@ def main():
     stage = {k: statistics.mean(v) for k, v in acc.items()}
 
     # PSNR of each view against the target, gathered over ranks (the only collective of the job)
-    mse = ((color - target) ** 2).mean(dim=(1, 2, 3))
-    psnr = gather_metric(-10 * torch.log10(mse))
+    from pf3plat_b200.metrics import compute_psnr
+    psnr = gather_metric(compute_psnr(target, color))
 
     if rank == 0:
         hbm, hbm_src = peaks()

@@ -173,6 +173,15 @@ GS_API int gs_get_stats(const GsContext *ctx, GsStats *out);
  */
 GS_API int gs_render_host(GsContext *ctx, const GsConfig *cfg, const GsInputs *in, const GsOutputs *out, void *stream);
 
+/*
+ * PSNR per image = compute_psnr of /root/reference/src/evaluation/metrics.py:11-19 (clip to [0,1], mean squared error
+ * over the n = c*h*w values of each image, -10 log10).  Device pointers: ground_truth, predicted [batch, n];
+ * scratch [gs_psnr_scratch_floats(batch, n)] floats; out [batch].  Deterministic (no atomics).
+ */
+GS_API int64_t gs_psnr_scratch_floats(int32_t batch, int64_t n);
+GS_API int gs_psnr(const float *ground_truth, const float *predicted, int32_t batch, int64_t n, float *scratch, float *out,
+            void *stream);
+
 /* Per-stage device timings (ms) of the last forward/backward when profiling is enabled; CUDA events on `stream`. */
 enum { GS_STAGE_PREPROCESS = 0,      /* k_preprocess (incl. tile counting) */
        GS_STAGE_BIN_SCAN = 1,        /* k_tile_scan + the forward's one host read-back */

@@ -72,6 +72,8 @@ SYMBOLS = {
     "gs_render_host": (c_int, [c_void_p, POINTER(GsConfig), POINTER(GsInputs), POINTER(GsOutputs), c_void_p]),
     "gs_set_profiling": (c_int, [c_void_p, c_int]),
     "gs_get_stage_ms": (c_int, [c_void_p, POINTER(c_float)]),
+    "gs_psnr_scratch_floats": (c_int64, [c_int32, c_int64]),
+    "gs_psnr": (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
 }
 
 

@@ -139,3 +139,17 @@ def test_host_buffer_entry_matches_device_entry():
     with pytest.raises(ValueError, match="SHs or precomputed colors"):
         _capi.check(_capi.lib().gs_render_host(ctx, ctypes.byref(cfg), ctypes.byref(bad), ctypes.byref(gout),
                                                torch.cuda.current_stream(dev).cuda_stream))
+
+
+def test_psnr_matches_the_reference_formula():
+    """compute_psnr against the reference's formula (src/evaluation/metrics.py:11-19) evaluated in fp64."""
+    from pf3plat_b200.metrics import compute_psnr
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(3)
+    for shape in [(5, 3, 37, 53), (2, 3, 256, 256), (1, 1, 1, 3)]:
+        gt = torch.rand(shape, generator=g) * 1.4 - 0.2          # exercises the clip on both sides
+        pr = torch.rand(shape, generator=g) * 1.4 - 0.2
+        ref = -10 * ((gt.double().clip(0, 1) - pr.double().clip(0, 1)) ** 2).flatten(1).mean(1).log10()
+        got = compute_psnr(gt.to(dev), pr.to(dev)).cpu().double()
+        assert torch.allclose(got, ref, atol=1e-4, rtol=0), (got, ref)
+        assert torch.equal(compute_psnr(gt.to(dev), pr.to(dev)).cpu().double(), got)     # deterministic
