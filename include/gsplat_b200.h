@@ -57,7 +57,9 @@ enum {
 };
 
 enum {
-    GS_TUNE_FORCE_RADIX_BINNING = 1u /* use the device-wide radix-sort binning even when every tile list fits shared memory */
+    GS_TUNE_FORCE_RADIX_BINNING = 1u, /* use the device-wide radix-sort binning even when every tile list fits shared memory */
+    GS_TUNE_NO_SPECULATION = 2u,      /* always size the tile buckets exactly (count + scan + emit passes, mid-call sync) */
+    GS_TUNE_SEPARATE_EMIT = 4u        /* speculative path: fill the buckets with k_emit_buckets even when they fit L2 */
 };
 
 /* GaussianRasterizationSettings (cuda_splatting.py:99-112), batched over views. */
@@ -134,6 +136,8 @@ typedef struct GsStats {
     int64_t scratch_bytes; /* bytes of grow-only scratch held by the context */
     int32_t kernel_launches; /* OUR kernels launched by the last forward (+ backward, if it followed); CUB's scan/sort launches are not counted */
     int32_t max_tile_list;   /* longest (view, tile) list of the last forward */
+    int32_t speculative;     /* 1 if the last forward ran on speculative bucket capacities (no count/scan/emit passes) */
+    int32_t reserved_;
 } GsStats;
 
 typedef struct GsContext GsContext; /* per (device, caller) workspace; not thread-safe, one call at a time */
@@ -149,8 +153,9 @@ GS_API void gs_context_destroy(GsContext *ctx);
 /*
  * Forward = _RasterizeGaussians.forward -> _C.rasterize_gaussians: preprocess,
  * bin/sort, composite.  If `saved` is non-NULL a handle for gs_backward is returned (free it with
- * gs_saved_free); pass NULL for inference.  Performs ONE host synchronisation per call (to size the tile
- * instance list), like upstream does per view.
+ * gs_saved_free); pass NULL for inference.  Performs ONE host synchronisation per call (upstream: one per view): on
+ * the first call of a shape it sizes the tile-instance list mid-way; later calls reuse the learned bucket capacities
+ * and only verify at the end that nothing overflowed (redoing the call exactly if it did).
  */
 GS_API int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *in, const GsOutputs *out, GsSaved **saved,
                void *stream);

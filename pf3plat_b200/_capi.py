@@ -17,6 +17,8 @@ ABI_VERSION = 1
 GS_FLAG_DEPTH = 1
 GS_FLAG_PREFILTERED = 2
 GS_TUNE_FORCE_RADIX_BINNING = 1
+GS_TUNE_NO_SPECULATION = 2
+GS_TUNE_SEPARATE_EMIT = 4
 GS_NUM_STAGES = 7
 STAGE_NAMES = ("preprocess", "bin_scan", "bin_emit", "bin_sort", "composite", "composite_bwd", "preprocess_bwd")
 
@@ -54,7 +56,8 @@ class GsInGrads(Structure):
 
 class GsStats(Structure):
     _fields_ = [("num_rendered", c_int64), ("num_visible", c_int64), ("saved_bytes", c_int64),
-                ("scratch_bytes", c_int64), ("kernel_launches", c_int32), ("max_tile_list", c_int32)]
+                ("scratch_bytes", c_int64), ("kernel_launches", c_int32), ("max_tile_list", c_int32),
+                ("speculative", c_int32), ("reserved_", c_int32)]
 
 
 # every symbol include/gsplat_b200.h declares: name -> (restype, argtypes)

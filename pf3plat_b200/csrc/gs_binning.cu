@@ -38,7 +38,8 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 constexpr int SCAN_THREADS = 1024;
 
 // counters[nvt * BIN_SUB] (padded: one per 32-byte sector) -> exclusive sub-bucket offsets[nvt * BIN_SUB],
-// per-tile totals tile_n[nvt], tile starts tile_start[nvt]; info[0] = total, info[1] = longest tile list
+// per-tile totals tile_n[nvt], tile starts tile_start[nvt]; info[0] = total, info[1] = longest tile list,
+// info[2] = largest sub-counter
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_tile_scan(int nvt, const uint32_t *__restrict__ counters, uint32_t *__restrict__ offsets,
             uint32_t *__restrict__ tile_start, uint32_t *__restrict__ tile_n, uint32_t *__restrict__ info) {
@@ -50,11 +51,15 @@ k_tile_scan(int nvt, const uint32_t *__restrict__ counters, uint32_t *__restrict
     } tmp;
     const int per = (nvt + SCAN_THREADS - 1) / SCAN_THREADS;  // tiles per thread
     const int b = threadIdx.x * per, e = min(nvt, b + per);
-    uint32_t sum = 0, mx = 0;
+    uint32_t sum = 0, mx = 0, mxs = 0;
     for (int t = b; t < e; t++) {
         uint32_t tn = 0;
 #pragma unroll
-        for (int k = 0; k < BIN_SUB; k++) tn += counters[((size_t)t * BIN_SUB + k) * BIN_PAD];
+        for (int k = 0; k < BIN_SUB; k++) {
+            const uint32_t cnt = counters[((size_t)t * BIN_SUB + k) * BIN_PAD];
+            tn += cnt;
+            mxs = max(mxs, cnt);
+        }
         sum += tn;
         mx = max(mx, tn);
     }
@@ -62,6 +67,8 @@ k_tile_scan(int nvt, const uint32_t *__restrict__ counters, uint32_t *__restrict
     BlockScan(tmp.scan).ExclusiveSum(sum, excl, total);
     __syncthreads();
     const uint32_t bmax = BlockReduce(tmp.reduce).Reduce(mx, cub::Max());
+    __syncthreads();
+    const uint32_t bmaxs = BlockReduce(tmp.reduce).Reduce(mxs, cub::Max());
     for (int t = b; t < e; t++) {
         tile_start[t] = excl;
         uint32_t tn = 0;
@@ -76,13 +83,14 @@ k_tile_scan(int nvt, const uint32_t *__restrict__ counters, uint32_t *__restrict
     if (threadIdx.x == 0) {
         info[0] = total;
         info[1] = bmax;
+        info[2] = bmaxs;
     }
 }
 
 __global__ void k_emit_buckets(const DevCfg c, const float4 *__restrict__ rec0, const float4 *__restrict__ rec1,
                                const float4 *__restrict__ rec2, const ushort4 *__restrict__ rects,
-                               const uint32_t *__restrict__ offsets, uint32_t *__restrict__ cursor,
-                               uint64_t *__restrict__ bucket) {
+                               const uint32_t *__restrict__ offsets, const uint32_t sub_cap,
+                               uint32_t *__restrict__ cursor, uint64_t *__restrict__ bucket) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (size_t)c.V * c.P) return;
     const ushort4 r = rects[g];
@@ -111,8 +119,11 @@ __global__ void k_emit_buckets(const DevCfg c, const float4 *__restrict__ rec0, 
         for (int k = 0; k < BATCH; k++)
             if (ok[k]) pos[k] = atomicAdd(&cursor[slot[k] * BIN_PAD], 1u);
 #pragma unroll
-        for (int k = 0; k < BATCH; k++)
-            if (ok[k]) bucket[(size_t)offsets[slot[k]] + pos[k]] = key;
+        for (int k = 0; k < BATCH; k++) {
+            if (!ok[k]) continue;
+            if (offsets) bucket[(size_t)offsets[slot[k]] + pos[k]] = key;                     // exact-capacity buckets
+            else if (pos[k] < sub_cap) bucket[slot[k] * (size_t)sub_cap + pos[k]] = key;     // fixed-capacity buckets
+        }
     }
 }
 
@@ -125,7 +136,8 @@ k_tile_sort(const uint32_t *__restrict__ tile_n, const uint32_t *__restrict__ ti
     const uint32_t n = tile_n[vt], off = tile_start[vt];
     if (threadIdx.x == 0) ranges[vt] = make_uint2(off, off + n);
     if (n == 0) return;
-    sort_bucket_dispatch<THREADS, MAX_ITEMS>(bucket + off, point_list + off, n, ts_smem);
+    const uint64_t *src = bucket + off;
+    sort_bucket_dispatch<THREADS, MAX_ITEMS>([src](uint32_t i) { return src[i]; }, point_list + off, n, ts_smem);
 }
 
 template <int THREADS, int MAX_ITEMS>
@@ -148,6 +160,92 @@ int dispatch_tile_sort(uint32_t max_count, int nvt, const uint32_t *tile_n, cons
     if (max_count <= THREADS * (CAP_ITEMS / 4)) return launch_tile_sort<THREADS, CAP_ITEMS / 4>(nvt, tile_n, tile_start, bucket, point_list, ranges, st);
     if (max_count <= THREADS * (CAP_ITEMS / 2)) return launch_tile_sort<THREADS, CAP_ITEMS / 2>(nvt, tile_n, tile_start, bucket, point_list, ranges, st);
     return launch_tile_sort<THREADS, CAP_ITEMS>(nvt, tile_n, tile_start, bucket, point_list, ranges, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// speculative-capacity path: preprocess has already appended the keys to fixed-capacity sub-buckets
+// (bucket[(vt * BIN_SUB + sub) * sub_cap + pos]); the cursors hold the counts.  k_spec_check turns the cursors
+// into the verdict (info: [0] total instances, [1] longest tile list, [2] largest sub-counter, [3] overflow flag);
+// k_tile_sort_spec gathers a tile's sub-buckets, sorts, and writes list + range.
+// ---------------------------------------------------------------------------------------------------------
+// One CTA: the verdict on a speculative forward, from the cursors alone (runs right after preprocess so that the
+// host can read it while the tile sort and the compositor are already enqueued behind it).
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_spec_check(int nvt, uint32_t sub_cap, uint32_t tile_limit, const uint32_t *__restrict__ cursor,
+             uint32_t *__restrict__ info) {
+    using BlockReduce = cub::BlockReduce<uint32_t, SCAN_THREADS>;
+    __shared__ typename BlockReduce::TempStorage tmp;
+    uint32_t sum = 0, mx = 0, mxs = 0, over = 0;
+    for (int t = threadIdx.x; t < nvt; t += SCAN_THREADS) {
+        uint32_t tn = 0;
+#pragma unroll
+        for (int k = 0; k < BIN_SUB; k++) {
+            const uint32_t cnt = cursor[((size_t)t * BIN_SUB + k) * BIN_PAD];
+            mxs = max(mxs, cnt);
+            over |= cnt > sub_cap ? 1u : 0u;
+            tn += cnt;
+        }
+        over |= tn > tile_limit ? 1u : 0u;
+        sum += tn;
+        mx = max(mx, tn);
+    }
+    const uint32_t total = BlockReduce(tmp).Sum(sum);
+    __syncthreads();
+    const uint32_t bmax = BlockReduce(tmp).Reduce(mx, cub::Max());
+    __syncthreads();
+    const uint32_t bmaxs = BlockReduce(tmp).Reduce(mxs, cub::Max());
+    __syncthreads();
+    const uint32_t bover = BlockReduce(tmp).Reduce(over, cub::Max());
+    if (threadIdx.x == 0) {
+        info[0] = total;
+        info[1] = bmax;
+        info[2] = bmaxs;
+        info[3] = bover;
+    }
+}
+
+template <int THREADS, int MAX_ITEMS>
+__global__ void __launch_bounds__(THREADS)
+k_tile_sort_spec(uint32_t sub_cap, const uint32_t *__restrict__ cursor, const uint64_t *__restrict__ bucket,
+                 uint32_t *__restrict__ point_list, uint2 *__restrict__ ranges) {
+    extern __shared__ __align__(16) unsigned char ts_smem[];
+    __shared__ uint32_t s_start[BIN_SUB + 1];
+    const uint32_t vt = blockIdx.x;
+    if (threadIdx.x == 0) {
+        uint32_t n = 0;
+        for (int k = 0; k < BIN_SUB; k++) {
+            s_start[k] = n;
+            n += min(cursor[((size_t)vt * BIN_SUB + k) * BIN_PAD], sub_cap);  // clamped: an overflowed call is redone
+        }
+        n = min(n, (uint32_t)(THREADS * MAX_ITEMS));
+        s_start[BIN_SUB] = n;
+        const uint32_t off = vt * BIN_SUB * sub_cap;
+        ranges[vt] = make_uint2(off, off + n);
+    }
+    __syncthreads();
+    const uint32_t n = s_start[BIN_SUB];
+    if (n == 0) return;
+    uint32_t st[BIN_SUB + 1];
+#pragma unroll
+    for (int k = 0; k <= BIN_SUB; k++) st[k] = s_start[k];
+    const uint64_t *base = bucket + (size_t)vt * BIN_SUB * sub_cap;
+    auto load = [&](uint32_t i) {
+        int k = 0;
+#pragma unroll
+        for (int j = 1; j < BIN_SUB; j++) k += (i >= st[j]) ? 1 : 0;  // sub-bucket holding logical entry i
+        return base[(size_t)k * sub_cap + (i - st[k])];
+    };
+    sort_bucket_dispatch<THREADS, MAX_ITEMS>(load, point_list + (size_t)vt * BIN_SUB * sub_cap, n, ts_smem);
+}
+
+template <int THREADS, int MAX_ITEMS>
+int launch_tile_sort_spec(int nvt, uint32_t sub_cap, const uint32_t *cursor, const uint64_t *bucket, uint32_t *point_list,
+                          uint2 *ranges, cudaStream_t st) {
+    const size_t smem = tile_sort_smem_bytes<THREADS, MAX_ITEMS>();
+    GS_CUDA_OK(cudaFuncSetAttribute(k_tile_sort_spec<THREADS, MAX_ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tile_sort_spec<THREADS, MAX_ITEMS><<<nvt, THREADS, smem, st>>>(sub_cap, cursor, bucket, point_list, ranges);
+    GS_CUDA_OK(cudaGetLastError());
+    return GS_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -252,11 +350,12 @@ size_t bin_scratch_bytes(const DevCfg &c, int64_t D, bool fast) {
 }
 
 int bin_emit_fast(const DevCfg &c, int64_t D, const float4 *rec0, const float4 *rec1, const float4 *rec2,
-                  const ushort4 *rects, const uint32_t *offsets, uint32_t *cursor, void *scratch, cudaStream_t st) {
+                  const ushort4 *rects, const uint32_t *offsets, uint32_t sub_cap, uint32_t *cursor, void *scratch,
+                  cudaStream_t st) {
     if (D <= 0) return GS_OK;
     GS_CUDA_OK(cudaMemsetAsync(cursor, 0, bin_counter_bytes(c), st));
     const size_t n = (size_t)c.V * c.P;
-    k_emit_buckets<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c, rec0, rec1, rec2, rects, offsets, cursor,
+    k_emit_buckets<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c, rec0, rec1, rec2, rects, offsets, sub_cap, cursor,
                                                                  static_cast<uint64_t *>(scratch));
     GS_CUDA_OK(cudaGetLastError());
     return GS_OK;
@@ -272,6 +371,32 @@ int bin_sort_fast(const DevCfg &c, uint32_t max_count, const uint32_t *tile_star
     if (max_count > 2048) return dispatch_tile_sort<1024>(max_count, nvt, tile_n, tile_start, bucket, point_list, ranges, st);
     if (max_count > 1024) return dispatch_tile_sort<512>(max_count, nvt, tile_n, tile_start, bucket, point_list, ranges, st);
     return dispatch_tile_sort<256>(max_count, nvt, tile_n, tile_start, bucket, point_list, ranges, st);
+}
+
+// The launch configuration that sorts lists of up to tile_limit entries (lists longer than that make k_spec_check
+// raise the overflow flag, so the clamp inside the kernel never decides a result that is kept).
+static uint32_t spec_sort_capacity(uint32_t tile_limit) {
+    return tile_limit <= 1024 ? 1024u : tile_limit <= 2048 ? 2048u : tile_limit <= 4096 ? 4096u : 8192u;
+}
+
+int bin_spec_check(const DevCfg &c, uint32_t sub_cap, uint32_t tile_limit, const uint32_t *cursor, uint32_t *info,
+                   cudaStream_t st) {
+    const uint32_t cap = spec_sort_capacity(tile_limit);
+    k_spec_check<<<1, SCAN_THREADS, 0, st>>>(c.V * c.ntiles, sub_cap, cap, cursor, info);
+    GS_CUDA_OK(cudaGetLastError());
+    return GS_OK;
+}
+
+int bin_sort_spec(const DevCfg &c, uint32_t sub_cap, uint32_t tile_limit, const uint32_t *cursor, const void *bucket,
+                  uint32_t *point_list, uint2 *ranges, cudaStream_t st) {
+    const int nvt = c.V * c.ntiles;
+    const uint64_t *b = static_cast<const uint64_t *>(bucket);
+    switch (spec_sort_capacity(tile_limit)) {
+        case 1024: return launch_tile_sort_spec<256, 4>(nvt, sub_cap, cursor, b, point_list, ranges, st);
+        case 2048: return launch_tile_sort_spec<512, 4>(nvt, sub_cap, cursor, b, point_list, ranges, st);
+        case 4096: return launch_tile_sort_spec<1024, 4>(nvt, sub_cap, cursor, b, point_list, ranges, st);
+        default: return launch_tile_sort_spec<1024, 8>(nvt, sub_cap, cursor, b, point_list, ranges, st);
+    }
 }
 
 int bin_sort_fallback(const DevCfg &c, int64_t D, const float4 *rec0, const float4 *rec1, const float4 *rec2,

@@ -50,7 +50,16 @@ struct GsContext {
     GrowBuf per_gaussian;  // rects | tile counts / offsets / cursors ; backward: accumulators
     GrowBuf sort;          // buckets (fast path) or radix-sort buffers (fallback)
     GrowBuf host_stage;    // device mirror of host buffers (gs_render_host)
-    uint32_t *h_word = nullptr;  // pinned: [0] = tile instances, [1] = longest tile list
+    uint32_t *d_word = nullptr;  // device alias of h_word (mapped pinned memory)
+    uint32_t *h_word = nullptr;  // pinned, written by the device: [0] tile instances, [1] longest tile list, [2] largest sub-counter, [3] overflow
+    // speculative bucket capacities learned from the previous forward of the same shape (0 = none yet)
+    struct {
+        int V = 0, ntiles = 0;
+        uint32_t sub_cap = 0;     // capacity of one of a tile's BIN_SUB sub-buckets
+        uint32_t tile_limit = 0;  // list length the tile sort is launched for
+    } spec;
+    cudaEvent_t ev_pre = nullptr;   // "preprocess done" (speculative path: lets the radii copy start early)
+    cudaEvent_t ev_info = nullptr;  // "binning verdict copied to the host"
     // gs_render_host: radii are final once the forward's mid-way sync has passed, so their copy to the host
     // overlaps binning + compositing on a side stream
     cudaStream_t copy_stream = nullptr;
@@ -152,6 +161,20 @@ size_t saved_layout(GsSaved *s, const DevCfg &c, unsigned char *base) {
     return off;
 }
 
+// Capacities for the next forward of this shape: 30 % headroom over what this one needed.
+void learn_capacities(GsContext *ctx, const DevCfg &c, uint32_t max_tile, uint32_t max_sub) {
+    const uint32_t sub_cap = max_sub + max_sub * 3 / 10 + 16;
+    const uint32_t limit = max_tile + max_tile / 10 + 32;
+    if (limit > BIN_SMEM_CAP || (uint64_t)sub_cap * BIN_SUB * c.V * c.ntiles > 0xffffffffull) {
+        ctx->spec.sub_cap = 0;  // lists too long for the shared-memory sort (or offsets beyond 32 bits): exact path
+        return;
+    }
+    ctx->spec.V = c.V;
+    ctx->spec.ntiles = c.ntiles;
+    ctx->spec.sub_cap = sub_cap;
+    ctx->spec.tile_limit = limit;
+}
+
 }  // namespace
 
 extern "C" int gs_context_create(GsContext **out) {
@@ -168,10 +191,11 @@ extern "C" int gs_context_create(GsContext **out) {
         uint64_t keep = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
-    cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&ctx->h_word), 64);
+    cudaError_t e = cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_word), 64, cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer(reinterpret_cast<void **>(&ctx->d_word), ctx->h_word, 0);
     if (e != cudaSuccess) {
         delete ctx;
-        return gs_set_cuda_error(e, "cudaMallocHost", __FILE__, __LINE__);
+        return gs_set_cuda_error(e, "cudaHostAlloc", __FILE__, __LINE__);
     }
     *out = ctx;
     return GS_OK;
@@ -184,6 +208,8 @@ extern "C" void gs_context_destroy(GsContext *ctx) {
     ctx->sort.release();
     ctx->host_stage.release();
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->ev_pre) cudaEventDestroy(ctx->ev_pre);
+    if (ctx->ev_info) cudaEventDestroy(ctx->ev_info);
     if (ctx->h_word) cudaFreeHost(ctx->h_word);
     if (ctx->profiling)
         for (auto &e : ctx->ev) {
@@ -289,11 +315,110 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
         return code;
     };
 
+    // ---- speculative-capacity forward: no count/scan/emit passes and no mid-pipeline host sync ----
+    // Preprocess appends straight into fixed-capacity sub-buckets sized from the previous forward of this shape;
+    // the one host read-back moves to the END of the call and only verifies that nothing overflowed.  On overflow
+    // the call is redone below on the exact path (and the capacities are re-learned).
+    const bool speculate = ctx->spec.sub_cap > 0 && ctx->spec.V == c.V && ctx->spec.ntiles == c.ntiles && n > 0 &&
+                           !(cfg->tuning & (GS_TUNE_FORCE_RADIX_BINNING | GS_TUNE_NO_SPECULATION));
+    if (speculate) {
+        const uint32_t sub_cap = ctx->spec.sub_cap;
+        const size_t slots = nvt * BIN_SUB;
+        rc = ctx->sort.reserve(slots * sub_cap * 8, 1.0);
+        if (rc != GS_OK) return fail(rc);
+        cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&s->point_list), slots * sub_cap * 4, st);
+        if (e != cudaSuccess) {
+            s->point_list = nullptr;
+            return fail(gs_set_cuda_error(e, "cudaMallocAsync(point_list)", __FILE__, __LINE__));
+        }
+        e = cudaMemsetAsync(cursor, 0, bin_counter_bytes(c), st);
+        if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "cudaMemsetAsync(cursors)", __FILE__, __LINE__));
+        // Appending from inside preprocess touches the buckets of ALL views at once; beyond L2 size those 8-byte
+        // appends turn into partial-sector DRAM writes (measured on C4: 4.5 ms fused vs 2.4 + 1.7 ms), so big bucket
+        // sets are filled by the view-major k_emit_buckets instead.
+        const bool fused_emit = slots * sub_cap * 8 <= ((size_t)96 << 20) && !(cfg->tuning & GS_TUNE_SEPARATE_EMIT);
+        {
+            StageTimer t(ctx, GS_STAGE_PREPROCESS, st);
+            const PreEmit emit{fused_emit ? cursor : nullptr, static_cast<uint64_t *>(ctx->sort.p), sub_cap};
+            rc = launch_preprocess(c, di, s->rec0, s->rec1, s->rec2, s->meta, out->radii, rects, emit, st);
+            if (rc != GS_OK) return fail(rc);
+        }
+        if (!fused_emit) {
+            StageTimer t(ctx, GS_STAGE_BIN_EMIT, st);
+            rc = bin_emit_fast(c, 1, s->rec0, s->rec1, s->rec2, rects, nullptr, sub_cap, cursor, ctx->sort.p, st);
+            if (rc != GS_OK) return fail(rc);
+        }
+        if (ctx->host_radii_dst && ctx->copy_stream) {  // radii leave for the host as soon as preprocess is done
+            if (!ctx->ev_pre) e = cudaEventCreateWithFlags(&ctx->ev_pre, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_pre, st);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_pre, 0);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(ctx->host_radii_dst, out->radii, ctx->host_radii_bytes, cudaMemcpyDeviceToHost,
+                                    ctx->copy_stream);
+            if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "early radii copy", __FILE__, __LINE__));
+        }
+        // The verdict (overflow flag, counts) follows from the cursors alone: one tiny kernel right after preprocess,
+        // its 16 bytes copied out and marked with an event.  The tile sort and the compositor are enqueued behind it
+        // BEFORE the host waits on that event, so the wait overlaps them and the caller gets control back (to
+        // enqueue its next call) while the GPU is still busy.
+        if (!ctx->ev_info) {
+            e = cudaEventCreateWithFlags(&ctx->ev_info, cudaEventDisableTiming);
+            if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "cudaEventCreate", __FILE__, __LINE__));
+        }
+        {
+            StageTimer t(ctx, GS_STAGE_BIN_SCAN, st);
+            // stored by the kernel straight into pinned host memory: an in-stream D2H copy would queue behind the
+            // 16 MB radii copy of gs_render_host in the copy engine and hold up the kernels enqueued after it
+            rc = bin_spec_check(c, sub_cap, ctx->spec.tile_limit, cursor, ctx->d_word, st);
+            if (rc != GS_OK) return fail(rc);
+            e = cudaEventRecord(ctx->ev_info, st);
+            if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "read back binning info", __FILE__, __LINE__));
+        }
+        {
+            StageTimer t(ctx, GS_STAGE_BIN_SORT, st);
+            rc = bin_sort_spec(c, sub_cap, ctx->spec.tile_limit, cursor, ctx->sort.p, s->point_list, s->ranges, st);
+            if (rc != GS_OK) return fail(rc);
+        }
+        {
+            StageTimer t(ctx, GS_STAGE_COMPOSITE, st);
+            rc = launch_composite_fwd(c, *s, out->color, out->depth, st);
+            if (rc != GS_OK) return fail(rc);
+        }
+        e = cudaEventSynchronize(ctx->ev_info);  // the one host sync of the forward (verification only)
+        if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "cudaEventSynchronize", __FILE__, __LINE__));
+        if (ctx->h_word[3] == 0) {
+            const int64_t D = (int64_t)ctx->h_word[0];
+            learn_capacities(ctx, c, ctx->h_word[1], ctx->h_word[2]);
+            s->D = D;
+            s->P = c.P; s->S = c.S; s->V = c.V; s->H = c.H; s->W = c.W;
+            s->flags = c.flags;
+            s->has_sh = in->shs != nullptr;
+            s->has_scales = in->scales != nullptr;
+            ctx->stats.kernel_launches = 4 + (fused_emit ? 0 : 1);  // k_preprocess, [k_emit_buckets], k_spec_check, k_tile_sort_spec, k_composite_fwd
+            ctx->stats.max_tile_list = (int32_t)ctx->h_word[1];
+            ctx->stats.num_rendered = D;
+            ctx->stats.num_visible = -1;
+            ctx->stats.saved_bytes = (int64_t)(s->bytes + slots * sub_cap * 4);
+            ctx->stats.speculative = 1;
+            if (saved_out) *saved_out = s;
+            else gs_saved_free(ctx, s, stream);
+            return GS_OK;
+        }
+        // overflow: some sub-bucket or tile list outgrew its capacity.  Results are invalid; redo exactly.
+        ctx->spec.sub_cap = 0;
+        if (ctx->host_radii_dst && ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+        cudaFreeAsync(s->point_list, st);
+        s->point_list = nullptr;
+        for (bool &v : ctx->ev_valid) v = false;
+    }
+    ctx->stats.speculative = 0;
+
     {
         StageTimer t(ctx, GS_STAGE_PREPROCESS, st);
         cudaError_t e = cudaMemsetAsync(tile_counts, 0, bin_counter_bytes(c), st);
         if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "cudaMemsetAsync(tile_counts)", __FILE__, __LINE__));
-        rc = launch_preprocess(c, di, s->rec0, s->rec1, s->rec2, s->meta, out->radii, rects, tile_counts, st);
+        const PreEmit emit{tile_counts, nullptr, 0};
+        rc = launch_preprocess(c, di, s->rec0, s->rec1, s->rec2, s->meta, out->radii, rects, emit, st);
         if (rc != GS_OK) return fail(rc);
         ctx->stats.kernel_launches += (c.P > 0);
     }
@@ -302,13 +427,14 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     uint32_t max_count = 0;
     {
         StageTimer t(ctx, GS_STAGE_BIN_SCAN, st);
-        rc = bin_tile_scan(c, tile_counts, sub_offsets, tile_start, tile_n, info, st);
+        // the scan kernel stores its three result words straight into pinned host memory (no copy-engine hop)
+        rc = bin_tile_scan(c, tile_counts, sub_offsets, tile_start, tile_n, ctx->d_word, st);
         if (rc != GS_OK) return fail(rc);
-        cudaError_t e = cudaMemcpyAsync(ctx->h_word, info, 8, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the one host sync of the forward
+        cudaError_t e = cudaStreamSynchronize(st);  // the one host sync of the (exact) forward
         if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "read back num_rendered", __FILE__, __LINE__));
         D = (int64_t)ctx->h_word[0];
         max_count = ctx->h_word[1];
+        learn_capacities(ctx, c, max_count, ctx->h_word[2]);
         if (ctx->host_radii_dst && ctx->copy_stream) {  // preprocess has completed: radii can leave now
             e = cudaMemcpyAsync(ctx->host_radii_dst, out->radii, ctx->host_radii_bytes, cudaMemcpyDeviceToHost,
                                 ctx->copy_stream);
@@ -329,7 +455,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     {
         StageTimer t(ctx, GS_STAGE_BIN_EMIT, st);
         if (fast)
-            rc = bin_emit_fast(c, D, s->rec0, s->rec1, s->rec2, rects, sub_offsets, cursor, ctx->sort.p, st);
+            rc = bin_emit_fast(c, D, s->rec0, s->rec1, s->rec2, rects, sub_offsets, 0, cursor, ctx->sort.p, st);
         else
             rc = bin_sort_fallback(c, D, s->rec0, s->rec1, s->rec2, rects, ctx->sort.p, ctx->sort.bytes, s->point_list,
                                    s->ranges, st);

@@ -57,8 +57,15 @@ int gs_set_cuda_error(cudaError_t e, const char *what, const char *file, int lin
 int gs_set_error(int code, const char *msg);
 
 // ---- kernel launchers (one translation unit per stage) ----
+// How preprocess hands its tile instances to the binning stage.
+struct PreEmit {
+    uint32_t *counters;   // padded sub-counters [V*tiles*BIN_SUB*BIN_PAD], zeroed: counts (exact path) or cursors
+                          // (speculative path, fused emission); NULL = preprocess neither counts nor emits
+    uint64_t *bucket;     // fused speculative emission only: fixed-capacity sub-buckets [V*tiles*BIN_SUB][sub_cap]
+    uint32_t sub_cap;     // capacity of one sub-bucket (speculative path)
+};
 int launch_preprocess(const DevCfg &c, const DevInputs &in, float4 *rec0, float4 *rec1, float4 *rec2, uint8_t *meta,
-                      int32_t *radii, ushort4 *rects, uint32_t *tile_counters /* padded sub-counters, zeroed */, cudaStream_t st);
+                      int32_t *radii, ushort4 *rects, const PreEmit &emit, cudaStream_t st);
 int launch_mark_visible(const DevCfg &c, const float *means3D, uint8_t *present, cudaStream_t st);
 
 // binning (gs_binning.cu)
@@ -70,10 +77,16 @@ int bin_tile_scan(const DevCfg &c, const uint32_t *counters, uint32_t *offsets, 
                   uint32_t *info, cudaStream_t st);
 bool bin_fits_fast_path(uint32_t max_count);
 size_t bin_scratch_bytes(const DevCfg &c, int64_t D, bool fast);
+// offsets != NULL: exact-capacity buckets at offsets[slot]; offsets == NULL: fixed-capacity buckets at slot * sub_cap
 int bin_emit_fast(const DevCfg &c, int64_t D, const float4 *rec0, const float4 *rec1, const float4 *rec2,
-                  const ushort4 *rects, const uint32_t *offsets, uint32_t *cursor, void *scratch, cudaStream_t st);
+                  const ushort4 *rects, const uint32_t *offsets, uint32_t sub_cap, uint32_t *cursor, void *scratch,
+                  cudaStream_t st);
 int bin_sort_fast(const DevCfg &c, uint32_t max_count, const uint32_t *tile_start, const uint32_t *tile_n,
                   const void *scratch, uint32_t *point_list, uint2 *ranges, cudaStream_t st);
+int bin_spec_check(const DevCfg &c, uint32_t sub_cap, uint32_t tile_limit, const uint32_t *cursor, uint32_t *info,
+                   cudaStream_t st);
+int bin_sort_spec(const DevCfg &c, uint32_t sub_cap, uint32_t tile_limit, const uint32_t *cursor, const void *bucket,
+                  uint32_t *point_list, uint2 *ranges, cudaStream_t st);
 int bin_sort_fallback(const DevCfg &c, int64_t D, const float4 *rec0, const float4 *rec1, const float4 *rec2,
                       const ushort4 *rects, void *scratch, size_t scratch_bytes, uint32_t *point_list, uint2 *ranges,
                       cudaStream_t st);

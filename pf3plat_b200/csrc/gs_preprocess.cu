@@ -128,7 +128,7 @@ template <bool HAS_SH>
 __global__ void __launch_bounds__(PRE_THREADS)
 k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, float4 *__restrict__ rec1,
              float4 *__restrict__ rec2, uint8_t *__restrict__ meta, int32_t *__restrict__ radii,
-             ushort4 *__restrict__ rects, uint32_t *__restrict__ tile_counts) {
+             ushort4 *__restrict__ rects, const PreEmit emit) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PreSmem *sm = reinterpret_cast<PreSmem *>(smem_raw);
     float *sh_s = reinterpret_cast<float *>(smem_raw + PRE_SMEM_HDR);
@@ -199,13 +199,25 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
             }
             radii[o] = sp.radius;
             rects[o] = sp.rect;
-            // count this Gaussian into every (view, tile) list it will join (binning step 1: RED.ADD, no return;
-            // sub-counter i % BIN_SUB, one counter per 32-byte sector -- see gs_binning.cu)
+            // Hand this Gaussian to every (view, tile) list it joins.  Exact path: count it (RED.ADD, no return;
+            // k_emit_buckets appends it later, once the offsets are known).  Speculative path: append it now to the
+            // tile's fixed-capacity sub-bucket; an entry beyond the capacity is dropped and the overflow is detected
+            // from the cursor by k_tile_sort_spec (the call is then redone on the exact path).  Sub-bucket
+            // i % BIN_SUB, one counter per 32-byte sector -- see gs_binning.cu.  (With very many (view, tile) buckets the
+            // fused appends of all views thrash L2; gs_forward then passes counters = NULL and emits per view instead.)
+            const uint64_t key = ((uint64_t)__float_as_uint(sp.r2.y) << 32) | (uint32_t)i;
+            if (emit.counters)
             for (int ty = sp.rect.y; ty < sp.rect.w; ty++)
                 for (int tx = sp.rect.x; tx < sp.rect.z; tx++)
-                    if (gs_tile_reached(sp.r0, sp.r1, sp.r2, tx, ty))
-                        atomicAdd(&tile_counts[(((size_t)v * c.ntiles + ty * c.gx + tx) * BIN_SUB + (i & (BIN_SUB - 1))) * BIN_PAD],
-                                  1u);
+                    if (gs_tile_reached(sp.r0, sp.r1, sp.r2, tx, ty)) {
+                        const size_t slot = ((size_t)v * c.ntiles + ty * c.gx + tx) * BIN_SUB + (i & (BIN_SUB - 1));
+                        if (emit.bucket) {
+                            const uint32_t pos = atomicAdd(&emit.counters[slot * BIN_PAD], 1u);
+                            if (pos < emit.sub_cap) emit.bucket[slot * emit.sub_cap + pos] = key;
+                        } else {
+                            atomicAdd(&emit.counters[slot * BIN_PAD], 1u);
+                        }
+                    }
             meta[o] = (uint8_t)sp.meta;
         }
     }
@@ -227,15 +239,15 @@ __global__ void k_mark_visible(const DevCfg c, const float *__restrict__ means3D
 }  // namespace
 
 int launch_preprocess(const DevCfg &c, const DevInputs &in, float4 *rec0, float4 *rec1, float4 *rec2, uint8_t *meta,
-                      int32_t *radii, ushort4 *rects, uint32_t *tile_counts, cudaStream_t st) {
+                      int32_t *radii, ushort4 *rects, const PreEmit &emit, cudaStream_t st) {
     if (c.P == 0) return GS_OK;
     dim3 grid((c.P + PRE_THREADS - 1) / PRE_THREADS, c.S);
     if (in.shs) {
         size_t smem = PRE_SMEM_HDR + (size_t)PRE_THREADS * c.M * 12;
         GS_CUDA_OK(cudaFuncSetAttribute(k_preprocess<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_preprocess<true><<<grid, PRE_THREADS, smem, st>>>(c, in, rec0, rec1, rec2, meta, radii, rects, tile_counts);
+        k_preprocess<true><<<grid, PRE_THREADS, smem, st>>>(c, in, rec0, rec1, rec2, meta, radii, rects, emit);
     } else {
-        k_preprocess<false><<<grid, PRE_THREADS, PRE_SMEM_HDR, st>>>(c, in, rec0, rec1, rec2, meta, radii, rects, tile_counts);
+        k_preprocess<false><<<grid, PRE_THREADS, PRE_SMEM_HDR, st>>>(c, in, rec0, rec1, rec2, meta, radii, rects, emit);
     }
     GS_CUDA_OK(cudaGetLastError());
     return GS_OK;

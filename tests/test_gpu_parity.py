@@ -216,83 +216,34 @@ def _render_with_tuning(sc, dev, tuning):
 
 
 def test_binning_paths_agree_bit_for_bit():
-    """Shared-memory bucket sort (fast path) vs device-wide radix sort (fallback) give the same lists, hence the
-    same pixels; and a scene whose densest tile exceeds the shared-memory capacity takes the fallback by itself."""
-    from pf3plat_b200._capi import GS_TUNE_FORCE_RADIX_BINNING
+    """Exact-capacity buckets, speculative-capacity buckets (second call of a shape) and the device-wide radix-sort
+    fallback give the same lists, hence the same pixels; overflowing the learned capacities is detected and redone;
+    a scene whose densest tile exceeds the shared-memory sort capacity takes the radix fallback by itself."""
+    from pf3plat_b200._capi import GS_TUNE_FORCE_RADIX_BINNING, GS_TUNE_NO_SPECULATION, GS_TUNE_SEPARATE_EMIT
     dev = _dev()
     sc = make_scene(30000, 2, 64, 96, seed=7)
-    fast, st_fast = _render_with_tuning(sc, dev, 0)
+    exact, st_exact = _render_with_tuning(sc, dev, GS_TUNE_NO_SPECULATION)
+    first, st_first = _render_with_tuning(sc, dev, 0)          # learns (or already has) the capacities
+    spec, st_spec = _render_with_tuning(sc, dev, 0)            # runs on them, appending from inside preprocess
+    spec2, st_spec2 = _render_with_tuning(sc, dev, GS_TUNE_SEPARATE_EMIT)   # same, buckets filled by k_emit_buckets
+    assert st_spec2["speculative"] == 1 and torch.equal(exact, spec2)
     slow, st_slow = _render_with_tuning(sc, dev, GS_TUNE_FORCE_RADIX_BINNING)
-    assert st_fast["num_rendered"] == st_slow["num_rendered"] and st_fast["max_tile_list"] <= 8192
-    assert torch.equal(fast, slow)
+    assert st_exact["speculative"] == 0 and st_spec["speculative"] == 1 and st_slow["speculative"] == 0
+    assert st_exact["num_rendered"] == st_spec["num_rendered"] == st_slow["num_rendered"]
+    assert st_exact["max_tile_list"] == st_spec["max_tile_list"] <= 8192
+    assert torch.equal(exact, spec) and torch.equal(exact, slow) and torch.equal(exact, first)
+    # same shape (2 views, 24 tiles), 2.5x the Gaussians: the learned capacities overflow -> detected, redone exactly
+    dense = make_scene(75000, 2, 64, 96, seed=7)
+    got, st_got = _render_with_tuning(dense, dev, 0)
+    ref, _ = _render_with_tuning(dense, dev, GS_TUNE_NO_SPECULATION)
+    assert st_got["speculative"] == 0 and torch.equal(got, ref)
+    again, st_again = _render_with_tuning(dense, dev, 0)       # capacities re-learned from the exact pass
+    assert st_again["speculative"] == 1 and torch.equal(again, ref)
     # 40k Gaussians squeezed into the centre of a 32x32 image: > 8192 entries in one tile
-    dense = make_scene(40000, 1, 32, 32, seed=8)
-    dense.means[:, :2] *= 0.05
-    color, st = _render_with_tuning(dense, dev, 0)
-    assert st["max_tile_list"] > 8192
-    check_image(color[0], oracle_view(dense, 0), max_fragile_frac=0.2)
-
-
-@pytest.mark.parametrize("d_sh", [1, 4, 9, 16, 25])
-def test_every_sh_band_count(d_sh):
-    """shs with 1/4/9/16/25 coefficients per channel (sh_degree 0..4; the evaluator stops at band 3)."""
-    dev = _dev()
-    sc = make_scene(3000, 2, 48, 48, seed=40 + d_sh, d_sh=d_sh)
-    color, leaves = render_batch(sc, dev, requires_grad=True)
-    (color * torch.linspace(0, 1, color.numel(), device=dev).reshape(color.shape)).sum().backward()
-    gs = np.zeros((3000, d_sh, 3))
-    for v in range(2):
-        orc = oracle_view(sc, v)
-        check_image(color[v], orc)
-        dL = torch.linspace(0, 1, color.numel()).reshape(color.shape)[v].numpy()
-        gs += orc.backward(dL)["shs"]
-    assert relerr(leaves["sh"].grad[0].permute(0, 2, 1), gs) <= GRAD_TOL
-
-
-def test_two_scenes_scale_rotation_inputs_background_and_rescale():
-    """S = 2 scenes x 2 views each in ONE call, Gaussians given as scales + rotations with scale_modifier != 1, a
-    non-zero background (exercises the T_final * bg term of the backward) and near != 1 (in-kernel 1/near rescale)."""
-    from oracle.gs_oracle import OracleRender
-    from pf3plat_b200.cameras import make_view_batch
-    from pf3plat_b200.rasterizer import BatchSettings, rasterize_batch
-    dev = _dev()
-    P, hw, mod, near = 2500, (40, 64), 1.3, 0.5
-    scs = [make_scene(P, 2, *hw, seed=50 + k) for k in range(2)]
-    for s in scs:
-        s.near[:] = near
-        s.far[:] = 100 * near
-        s.background[:] = torch.tensor([0.3, 0.6, 0.1])
-    cat = lambda name: torch.cat([getattr(s, name) for s in scs]).to(dev)
-    vb = make_view_batch(cat("extrinsics"), cat("intrinsics"), cat("near"), cat("far"))
-    bs = BatchSettings(image_height=hw[0], image_width=hw[1], viewmatrix=vb.viewmatrix, projmatrix=vb.projmatrix,
-                       campos=vb.campos, bg=cat("background"), sh_degree=4, tanfov=vb.tanfov, view_scale=vb.scale,
-                       scale_modifier=mod)
-    st = lambda name: torch.stack([getattr(s, name) for s in scs]).to(dev)
-    leaves = {"means3D": st("means"), "opacities": st("opacities"), "shs": st("harmonics").permute(0, 1, 3, 2).contiguous(),
-              "scales": st("scales"), "rotations": st("rotations")}
-    for t in leaves.values():
-        t.requires_grad_(True)
-    color, radii = rasterize_batch(bs, **leaves)
-    target = make_target(4, *hw).to(dev)
-    ((color - target) ** 2).mean().backward()
-    for k, sc in enumerate(scs):
-        g = {n: 0 for n in ("means3D", "opacities", "shs", "scales", "rotations")}
-        for vi in range(2):
-            v = 2 * k + vi
-            stt, kw = view_args(sc, vi)
-            kw.pop("cov3D_precomp")
-            s = 1.0 / near                      # render_cuda's rescale, done outside for the oracle
-            kw["scales"] = sc.scales.numpy() * s
-            kw["rotations"] = sc.rotations.numpy()
-            stt.scale_modifier = mod
-            orc = OracleRender(stt, **kw)
-            check_image(color[v], orc)
-            check_radii(radii[v], orc)
-            dL = (2 * (orc.color - target[v].cpu().numpy()) / target.numel()).astype(np.float32)
-            go = orc.backward(dL)
-            g["means3D"] = g["means3D"] + go["means3D"] * s          # d(s*m)/dm
-            g["scales"] = g["scales"] + go["scales"] * s
-            for n in ("opacities", "shs", "rotations"):
-                g[n] = g[n] + go[n]
-        for n, ref in g.items():
-            assert relerr(leaves[n].grad[k], np.asarray(ref).reshape(leaves[n].grad[k].shape)) <= GRAD_TOL, n
+    huge = make_scene(40000, 1, 32, 32, seed=8)
+    huge.means[:, :2] *= 0.05
+    color, st = _render_with_tuning(huge, dev, 0)
+    assert st["max_tile_list"] > 8192 and st["speculative"] == 0
+    check_image(color[0], oracle_view(huge, 0), max_fragile_frac=0.2)
+    color2, st2 = _render_with_tuning(huge, dev, 0)            # lists too long to speculate on: still exact
+    assert st2["speculative"] == 0 and torch.equal(color, color2)
