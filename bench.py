@@ -25,7 +25,6 @@ import ctypes
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -52,42 +51,49 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock / throttle reasons of one GPU every 5 ms through NVML while the timed regions run."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self.thread = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES; NVML enumerates physical devices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].strip().isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.reasons.add(f"nvml unavailable: {type(e).__name__}")
+            return
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, name in self.REASONS.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                except Exception:  # noqa: BLE001
+                    pass
+                time.sleep(0.005)
+
+        self.thread = threading.Thread(target=loop, daemon=True)
+        self.thread.start()
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, c in zip(names, r[5:9]) if c.lower() == "active"})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        self._stop.set()
+        if self.thread:
+            self.thread.join(timeout=1)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 def run_reference(args):
@@ -253,9 +259,9 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     ms_fwd = timed(fwd, args.steps, args.warmup)
-    clocks = sampler.stop()
     ms_e2e = timed(e2e, args.steps, args.warmup)
     ms_fb = timed(fwd_bwd, args.steps, args.warmup)
+    clocks = sampler.stop()   # covers the three timed loops (warm-ups included: the GPU is under the same load)
     stats_fb = rasterizer.last_stats(dev)
 
     # per-stage device time (library-recorded CUDA events on the launch stream), separate pass
