@@ -259,6 +259,7 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     ms_fwd = timed(fwd, args.steps, args.warmup)
+    launches_fwd = rasterizer.last_stats(dev)["kernel_launches"]   # of the last timed step (steady state)
     ms_e2e = timed(e2e, args.steps, args.warmup)
     ms_fb = timed(fwd_bwd, args.steps, args.warmup)
     clocks = sampler.stop()   # covers the three timed loops (warm-ups included: the GPU is under the same load)
@@ -344,7 +345,8 @@ def main():
             "fwd_bwd": {"value": gauss_per_step * args.steps / (ms_fb * 1e-3), "unit": "Gaussians/s",
                         "ms_per_step": ms_fb / args.steps, "loss": "MSE to U(0,1) target"},
             "gpu_launches": (launches_fwd) * args.steps,
-            "gpu_launches_note": f"{launches_fwd} own kernels per forward step (+ CUB scan/sort); fwd+bwd step: "
+            "gpu_launches_note": f"{launches_fwd} own kernels per forward step (k_preprocess, k_spec_check, "
+                                 f"k_tile_sort_spec, k_composite_fwd in steady state); fwd+bwd step: "
                                  f"{stats_fb['kernel_launches']}",
             "roofline": {"kernel": dom, "bound": "hbm", "achieved": dom_gbs, "peak": hbm, "unit": "GB/s",
                          "frac": dom_gbs / hbm, "traffic": traffic, "peak_source": hbm_src,

@@ -247,3 +247,22 @@ def test_binning_paths_agree_bit_for_bit():
     check_image(color[0], oracle_view(huge, 0), max_fragile_frac=0.2)
     color2, st2 = _render_with_tuning(huge, dev, 0)            # lists too long to speculate on: still exact
     assert st2["speculative"] == 0 and torch.equal(color, color2)
+
+
+def test_pixel_aligned_pf3plat_shaped_cloud():
+    """2 x 128 x 128 pixel-aligned Gaussians (the structure PF3plat's encoder emits): neighbouring indices share
+    tiles, lists are short, many splats are sub-pixel.  Forward and backward against the oracle."""
+    from pf3plat_b200.synthetic import make_pixel_aligned_scene
+    dev = _dev()
+    sc = make_pixel_aligned_scene(128, 128, 3, seed=2)
+    assert sc.means.shape[0] == 2 * 128 * 128
+    color, leaves = render_batch(sc, dev, requires_grad=True)
+    target = make_target(3, 128, 128).to(dev)
+    ((color - target) ** 2).mean().backward()
+    gm = 0
+    for v in range(3):
+        orc = oracle_view(sc, v)
+        check_image(color[v], orc)
+        dL = (2 * (orc.color - target[v].cpu().numpy()) / target.numel()).astype(np.float32)
+        gm = gm + orc.backward(dL)["means3D"]
+    assert relerr(leaves["means"].grad[0], gm) <= GRAD_TOL
