@@ -103,9 +103,10 @@ k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
                 const uint2 *__restrict__ ranges, const float *__restrict__ final_T,
                 const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dcolor,
                 const float *__restrict__ dL_ddepth, float *__restrict__ acc) {
-    __shared__ float4 s_cull[CB_BATCH];    // (hC, reach2, -, -): with s_rec[.][0] all the exact box test needs
-    __shared__ float4 s_rec[CB_BATCH][3];  // rec0 | rec1 | rec2, read as warp-wide broadcasts
-    __shared__ uint32_t sid[CB_BATCH];
+    // double-buffered staging, as in the forward: the cp.async gathers of the next batch land in one buffer while the
+    // warps walk the other
+    __shared__ float4 s_rec[2][CB_BATCH][3];  // rec0 | rec1 | rec2, read as warp-wide broadcasts
+    __shared__ uint32_t s_id[2][CB_BATCH];    // Gaussian index of every staged entry (target of the atomics)
     __shared__ uint32_t s_max[CB_THREADS / 32];
 
     const int v = blockIdx.y;
@@ -118,7 +119,7 @@ k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
     const float pxf = (float)px, pyf = (float)py;
     const float bx0 = (float)bx, bx1 = (float)(bx + 7), by0 = (float)by, by1 = (float)(by + 3);
     const float half_w = 0.5f * (float)c.W, half_h = 0.5f * (float)c.H;
-    const uint32_t cull_addr = smem_u32(&s_cull[0]), rec_addr = smem_u32(&s_rec[0][0]);
+    const uint32_t stage_addr = smem_u32(&s_rec[0][0][0]);
 
     const uint2 range = ranges[(size_t)v * c.ntiles + tile];
     const size_t rbase = (size_t)v * c.P;
@@ -155,29 +156,44 @@ k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
 #pragma unroll
     for (int w = 0; w < CB_THREADS / 32; w++) cta_last = max(cta_last, s_max[w]);
 
-    for (uint32_t hi = cta_last; hi > 0; hi -= min(hi, (uint32_t)CB_BATCH)) {
-        const uint32_t lo = hi > CB_BATCH ? hi - CB_BATCH : 0u;  // list positions [lo, hi), relative to range.x
-        const uint32_t nb = hi - lo;
-        __syncthreads();  // previous batch fully consumed
-        if ((uint32_t)tid < nb) {
-            const uint32_t id = point_list[range.x + lo + tid];
+    // batch k covers list positions [lo_k, hi_k), hi_k = cta_last - k * CB_BATCH, walked from the back
+    const uint32_t nbatches = (cta_last + CB_BATCH - 1) / CB_BATCH;
+    auto batch_lo = [&](uint32_t k) { const uint32_t hi = cta_last - k * CB_BATCH; return hi > CB_BATCH ? hi - CB_BATCH : 0u; };
+    auto load_id = [&](uint32_t k) -> uint32_t {
+        if (k >= nbatches) return 0u;
+        const uint32_t e = batch_lo(k) + tid;
+        return e < cta_last - k * CB_BATCH ? point_list[range.x + e] : 0u;
+    };
+    auto gather = [&](uint32_t k, uint32_t id) {
+        if (k < nbatches && batch_lo(k) + tid < cta_last - k * CB_BATCH) {
             const size_t r = rbase + id;
-            const float4 q0 = rec0[r], q1 = rec1[r], q2 = rec2[r];
-            sid[tid] = id;
-            s_cull[tid] = make_float4(q1.x, q2.z, 0.f, 0.f);
-            s_rec[tid][0] = q0;
-            s_rec[tid][1] = q1;
-            s_rec[tid][2] = q2;
+            float4 *dst = &s_rec[k & 1][tid][0];
+            cp_async16(dst, rec0 + r);
+            cp_async16(dst + 1, rec1 + r);
+            cp_async16(dst + 2, rec2 + r);
+            s_id[k & 1][tid] = id;
         }
-        __syncthreads();
+        cp_async_commit();  // one group per batch, empty or not
+    };
+    gather(0, load_id(0));
+    uint32_t id_next = load_id(1);
+    for (uint32_t k = 0; k < nbatches; k++) {
+        const uint32_t hi = cta_last - k * CB_BATCH, lo = batch_lo(k), nb = hi - lo;
+        __syncthreads();  // batch k-1 fully consumed: its buffer may be overwritten
+        gather(k + 1, id_next);
+        id_next = load_id(k + 2);
+        cp_async_wait<1>();  // this thread's part of batch k has landed ...
+        __syncthreads();     // ... and so has everybody else's
+        const uint32_t rec_addr = stage_addr + (k & 1u) * (uint32_t)sizeof(s_rec[0]);
+        const uint32_t *sid = s_id[k & 1];
         if (lo >= warp_last) continue;  // nothing in this batch is below any of this warp's last contributors
         for (int chunk = (int)((nb - 1) & ~31u); chunk >= 0; chunk -= 32) {
             const uint32_t j = (uint32_t)chunk + lane;
             bool hit = false;
             if (j < nb && lo + j < warp_last) {
-                const float4 g0 = lds128(rec_addr + j * 48u);
-                const float2 g1 = lds64(cull_addr + j * 16u);
-                hit = gs_box_reaches(g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, bx0, bx1, by0, by1);
+                const uint32_t a = rec_addr + j * 48u;
+                const float4 g0 = lds128(a);
+                hit = gs_box_reaches(g0.x, g0.y, g0.z, g0.w, lds32(a + 16u), lds32(a + 40u), bx0, bx1, by0, by1);
             }
             uint32_t mask = __ballot_sync(0xffffffffu, hit);
             while (mask) {
@@ -212,6 +228,7 @@ k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
             }
         }
     }
+    cp_async_wait<0>();  // nothing of ours may still be in flight into shared memory when the CTA retires
 }
 
 }  // namespace

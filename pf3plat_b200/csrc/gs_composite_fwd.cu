@@ -5,10 +5,11 @@
 // when T*(1-alpha) < 1e-4; C += c*alpha*T; out = C + T*bg; keep final T and the last contributor's position.
 //
 // B200 design.  One CTA per (view, 16x16 tile), 8 warps, each warp owning an 8x4 pixel
-// block.  A batch of 256 splat records is gathered into shared memory with 16-byte loads; then every warp
-// CULLS the batch against its own 8x4 block 32 Gaussians at a time -- lane k tests Gaussian k's alpha>=1/255
-// bounding box, one ballot yields the survivors -- and only survivors are evaluated by the 32 pixel lanes
-// (shared-memory broadcast reads).  With PF3plat-sized splats (sigma 0.1-3 px) this removes ~10x of the
+// block.  Batches of 256 splat records are gathered into a double-buffered shared-memory stage with 16-byte
+// cp.async copies (LDGSTS), the next batch in flight while the current one is composited; every warp
+// CULLS the batch against its own 8x4 block 32 Gaussians at a time -- lane k tests whether Gaussian k's
+// alpha>=1/255 ellipse reaches the block (gs_box_reaches, exact), one ballot yields the survivors -- and only
+// survivors are evaluated by the 32 pixel lanes (shared-memory broadcast reads).  With PF3plat-sized splats (sigma 0.1-3 px) this removes ~10x of the
 // (pixel, Gaussian) pair evaluations that the reference design spends on alpha < 1/255 rejections, without
 // changing a single pixel: a culled Gaussian fails the alpha test at every pixel of the block.
 //
@@ -26,10 +27,10 @@ namespace {
 constexpr int CF_THREADS = 256;
 constexpr int CF_BATCH = 256;
 
-// Shared-memory staging of one batch: per Gaussian a 16-byte cull record and a 48-byte evaluation record.
-struct CfBatch {
-    float4 cull[CF_BATCH];     // (hC, reach2, -, -): with rec[.][0] all the exact box test needs; lane k reads entry k
-    float4 rec[CF_BATCH][3];   // rec0 | rec1 | rec2 of gs_common.cuh, read as warp-wide broadcasts
+// Shared-memory staging: two buffers of one batch each (48-byte records rec0 | rec1 | rec2 of gs_common.cuh).
+// While the warps composite batch b out of one buffer, the cp.async (LDGSTS) gathers of batch b+1 land in the other.
+struct CfStage {
+    float4 rec[CF_BATCH][3];
 };
 
 template <bool DEPTH>
@@ -38,7 +39,7 @@ k_composite_fwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
                 const float4 *__restrict__ rec2, const uint32_t *__restrict__ point_list,
                 const uint2 *__restrict__ ranges, float *__restrict__ color, float *__restrict__ depth,
                 float *__restrict__ final_T, uint32_t *__restrict__ n_contrib) {
-    __shared__ CfBatch sm;
+    __shared__ CfStage stage[2];
 
     const int v = blockIdx.y;
     const int tile = blockIdx.x;
@@ -51,43 +52,60 @@ k_composite_fwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
     const float bx0 = (float)bx, bx1 = (float)(bx + 7), by0 = (float)by, by1 = (float)(by + 3);
 
     const uint2 range = ranges[(size_t)v * c.ntiles + tile];
+    const uint32_t total = range.y - range.x;
+    const uint32_t nbatches = (total + CF_BATCH - 1) / CF_BATCH;
     const size_t rbase = (size_t)v * c.P;
-    const uint32_t cull_addr = smem_u32(&sm.cull[0]), rec_addr = smem_u32(&sm.rec[0][0]);
+    const uint32_t stage_addr = smem_u32(&stage[0].rec[0][0]);
+
+    // gather the records of batch b (this thread: list entry b * CF_BATCH + tid, whose index is `id`) into its buffer
+    auto gather = [&](uint32_t b, uint32_t id) {
+        if (b * CF_BATCH + tid < total) {
+            const size_t r = rbase + id;
+            float4 *dst = &stage[b & 1].rec[tid][0];
+            cp_async16(dst, rec0 + r);
+            cp_async16(dst + 1, rec1 + r);
+            cp_async16(dst + 2, rec2 + r);
+        }
+        cp_async_commit();  // one group per batch, empty or not, so that wait_group<1> always means "batch b landed"
+    };
+    auto load_id = [&](uint32_t b) -> uint32_t {
+        const uint32_t e = b * CF_BATCH + tid;
+        return e < total ? point_list[range.x + e] : 0u;
+    };
 
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dz = 0.f;
     uint32_t last = 0;
     bool done = !inside;
     bool warp_done = false;
 
-    for (uint32_t base = range.x; base < range.y; base += CF_BATCH) {
-        if (__syncthreads_and(done)) break;  // also protects the staging buffers of the previous batch
-        const uint32_t nb = min((uint32_t)CF_BATCH, range.y - base);
-        if ((uint32_t)tid < nb) {
-            const size_t r = rbase + point_list[base + tid];
-            const float4 q0 = rec0[r], q1 = rec1[r], q2 = rec2[r];
-            sm.cull[tid] = make_float4(q1.x, q2.z, 0.f, 0.f);
-            sm.rec[tid][0] = q0;
-            sm.rec[tid][1] = q1;
-            sm.rec[tid][2] = q2;
-        }
-        __syncthreads();
+    gather(0, load_id(0));
+    uint32_t id_next = load_id(1);  // index for the batch after the one in flight: its latency hides behind a whole batch
+    for (uint32_t b = 0; b < nbatches; b++) {
+        // everybody is past batch b-1 (so its buffer may be overwritten); stop when every pixel of the tile is done
+        if (__syncthreads_and(done)) break;
+        gather(b + 1, id_next);
+        id_next = load_id(b + 2);
+        cp_async_wait<1>();  // this thread's part of batch b has landed ...
+        __syncthreads();     // ... and so has everybody else's
         if (warp_done) continue;
-        const uint32_t pos0 = base - range.x + 1;  // 1-based list position of this batch's first entry
+        const uint32_t nb = min((uint32_t)CF_BATCH, total - b * CF_BATCH);
+        const uint32_t pos0 = b * CF_BATCH + 1;  // 1-based list position of this batch's first entry
+        const uint32_t rec_addr = stage_addr + (b & 1u) * (uint32_t)sizeof(CfStage);
         for (uint32_t chunk = 0; chunk < nb; chunk += 32) {
             const uint32_t j = chunk + lane;
             bool hit = false;
             if (j < nb) {
                 // exact: does the alpha >= 1/255 ellipse reach this warp's 8x4 block?
-                const float4 g0 = lds128(rec_addr + j * 48u);
-                const float2 g1 = lds64(cull_addr + j * 16u);
-                hit = gs_box_reaches(g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, bx0, bx1, by0, by1);
+                const uint32_t a = rec_addr + j * 48u;
+                const float4 g0 = lds128(a);
+                hit = gs_box_reaches(g0.x, g0.y, g0.z, g0.w, lds32(a + 16u), lds32(a + 40u), bx0, bx1, by0, by1);
             }
             uint32_t mask = __ballot_sync(0xffffffffu, hit);
             const uint32_t chunk_addr = rec_addr + chunk * 48u;
             while (mask) {
-                const uint32_t b = (uint32_t)__ffs(mask) - 1u;
+                const uint32_t bit = (uint32_t)__ffs(mask) - 1u;
                 mask &= mask - 1u;
-                const uint32_t a = chunk_addr + b * 48u;
+                const uint32_t a = chunk_addr + bit * 48u;
                 const float4 q0 = lds128(a), q1 = lds128(a + 16u);
                 const float dx = q0.x - pxf, dy = q0.y - pyf;
                 const float p2 = gs_power2(q0.z, q0.w, q1.x, dx, dy);
@@ -105,7 +123,7 @@ k_composite_fwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
                         C2 = fmaf(q2.x, w, C2);
                         if (DEPTH) Dz = fmaf(q2.y, w, Dz);
                         T = test_T;
-                        last = pos0 + chunk + b;
+                        last = pos0 + chunk + bit;
                     }
                 }
             }
@@ -115,6 +133,7 @@ k_composite_fwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
             }
         }
     }
+    cp_async_wait<0>();  // nothing of ours may still be in flight into shared memory when the CTA retires
 
     if (inside) {
         const size_t hw = (size_t)c.H * c.W;
