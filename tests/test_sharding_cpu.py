@@ -10,7 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from pf3plat_b200.cameras import make_view_batch
-from pf3plat_b200.sharding import gather_metric, shard_views
+from pf3plat_b200.sharding import allreduce_scene_gradients, gather_metric, shard_views
 from pf3plat_b200.synthetic import make_scene
 
 
@@ -28,7 +28,10 @@ def _worker(rank, world, port, out):
         psnr_local = torch.tensor([float(v) for v in views])
         allp = gather_metric(psnr_local)
         sc = make_scene(100, len(views), 32, 32, first_view=views[0], total_views=8)
-        out.put((rank, views, allp.tolist(), sc.extrinsics[:, :2, 3].tolist()))
+        # one scene's views split over the ranks: per-Gaussian gradient blocks are summed by ONE all-reduce
+        g_means, g_sh = torch.full((100, 3), float(rank + 1)), torch.full((100, 25, 3), 10.0 * (rank + 1))
+        allreduce_scene_gradients([g_means, None, g_sh])
+        out.put((rank, views, allp.tolist(), sc.extrinsics[:, :2, 3].tolist(), float(g_means[7, 1]), float(g_sh[3, 2, 1])))
     finally:
         dist.destroy_process_group()
 
@@ -44,7 +47,8 @@ def test_view_sharding_and_psnr_gather_world2():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (r0, v0, g0, t0), (r1, v1, g1, t1) = res
+    (r0, v0, g0, t0, m0, s0), (r1, v1, g1, t1, m1, s1) = res
+    assert m0 == m1 == 3.0 and s0 == s1 == 30.0                    # 1 + 2 and 10 + 20 on both ranks
     assert v0 == [0, 1, 2, 3] and v1 == [4, 5, 6, 7]               # contiguous, disjoint, complete
     assert g0 == g1 == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0]    # every rank sees every view's metric, in view order
     full = make_scene(100, 8, 32, 32).extrinsics[:, :2, 3].tolist()
