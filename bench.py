@@ -105,8 +105,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    from oracle import gs_oracle
+    cores = gs_oracle.set_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1: ask for all cores
     sc = make_scene(P_GAUSS, VIEWS, HW, HW, seed=0)
     for _ in range(args.warmup):
         st, kw = view_args(sc, 0)
@@ -284,10 +284,11 @@ def main():
         # CPU baseline on a bounded sample + the oracle's own D (upstream's 3-sigma-square definition)
         cpu = None
         D_ref_per_view = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # contract: the CPU baseline leg runs at N = 1 only
+            from oracle import gs_oracle
             from oracle.gs_oracle import OracleRender
             from tests.util import view_args
-            cores = os.cpu_count() or 1
+            cores = gs_oracle.set_threads(os.cpu_count() or 1)
             nv = 2
             t0 = time.perf_counter()
             Ds = []

@@ -272,6 +272,21 @@ void gso_free(gso_handle *h) {
     free(h);
 }
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+/* Number of OpenMP threads the oracle uses from now on (torchrun exports OMP_NUM_THREADS=1 to its children; the
+ * CPU-baseline legs of bench.py ask for all host cores explicitly).  Returns the value in effect. */
+int gso_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 int gso_real_size(void) { return (int)sizeof(real); }
 int gso_params_size(void) { return (int)sizeof(gso_params); }
 

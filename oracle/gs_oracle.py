@@ -28,6 +28,11 @@ def build() -> None:
     subprocess.run(["make", "-s", "-C", _HERE], check=True)
 
 
+def set_threads(n: int) -> int:
+    """Sets the OpenMP thread count of both oracle libraries; returns the count in effect (1 without OpenMP)."""
+    return min(int(_lib(d).gso_set_threads(int(n))) for d in (np.float32, np.float64))
+
+
 def _lib(dtype) -> ctypes.CDLL:
     name = "f64" if np.dtype(dtype) == np.float64 else "f32"
     if name not in _LIBS:
@@ -40,6 +45,8 @@ def _lib(dtype) -> ctypes.CDLL:
         lib.gso_backward.restype = None
         lib.gso_backward.argtypes = [ctypes.c_void_p] * 11
         lib.gso_free.argtypes = [ctypes.c_void_p]
+        lib.gso_set_threads.restype = ctypes.c_int
+        lib.gso_set_threads.argtypes = [ctypes.c_int]
         for f in ("gso_num_rendered", "gso_num_visible", "gso_num_pairs"):
             getattr(lib, f).restype = ctypes.c_int64
             getattr(lib, f).argtypes = [ctypes.c_void_p]
