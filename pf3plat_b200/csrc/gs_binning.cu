@@ -230,10 +230,14 @@ k_tile_sort_spec(uint32_t sub_cap, const uint32_t *__restrict__ cursor, const ui
     for (int k = 0; k <= BIN_SUB; k++) st[k] = s_start[k];
     const uint64_t *base = bucket + (size_t)vt * BIN_SUB * sub_cap;
     auto load = [&](uint32_t i) {
-        int k = 0;
+        uint32_t k = 0, first = 0;  // sub-bucket holding logical entry i and that sub-bucket's first logical entry
 #pragma unroll
-        for (int j = 1; j < BIN_SUB; j++) k += (i >= st[j]) ? 1 : 0;  // sub-bucket holding logical entry i
-        return base[(size_t)k * sub_cap + (i - st[k])];
+        for (int j = 1; j < BIN_SUB; j++)
+            if (i >= st[j]) {
+                k = (uint32_t)j;
+                first = st[j];
+            }
+        return base[(size_t)k * sub_cap + (i - first)];
     };
     sort_bucket_dispatch<THREADS, MAX_ITEMS>(load, point_list + (size_t)vt * BIN_SUB * sub_cap, n, ts_smem);
 }

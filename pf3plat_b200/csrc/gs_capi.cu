@@ -273,10 +273,10 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     for (bool &v : ctx->ev_valid) v = false;
     ctx->stats.kernel_launches = 0;
 
-    // ---- per-call scratch: rects[n] | counters | cursors | sub-bucket offsets | tile_start | tile_n | info ----
+    // ---- per-call scratch: rects[n] | counters | cursors | sub-bucket offsets | tile_start | tile_n ----
     const size_t nvt = (size_t)c.V * c.ntiles;
     const size_t ctr_bytes = align256(bin_counter_bytes(c));
-    const size_t pg_bytes = align256(n * 8) + 2 * ctr_bytes + align256(nvt * BIN_SUB * 4) + 2 * align256(nvt * 4) + 256;
+    const size_t pg_bytes = align256(n * 8) + 2 * ctr_bytes + align256(nvt * BIN_SUB * 4) + 2 * align256(nvt * 4);
     rc = ctx->per_gaussian.reserve(pg_bytes, 1.0);
     if (rc != GS_OK) return rc;
     unsigned char *pg = static_cast<unsigned char *>(ctx->per_gaussian.p);
@@ -291,8 +291,6 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     uint32_t *tile_start = reinterpret_cast<uint32_t *>(pg);
     pg += align256(nvt * 4);
     uint32_t *tile_n = reinterpret_cast<uint32_t *>(pg);
-    pg += align256(nvt * 4);
-    uint32_t *info = reinterpret_cast<uint32_t *>(pg);
 
     // ---- saved state: geometry / image planes now, the tile-instance list once its length is known ----
     GsSaved *s = new (std::nothrow) GsSaved();
@@ -315,10 +313,11 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
         return code;
     };
 
-    // ---- speculative-capacity forward: no count/scan/emit passes and no mid-pipeline host sync ----
-    // Preprocess appends straight into fixed-capacity sub-buckets sized from the previous forward of this shape;
-    // the one host read-back moves to the END of the call and only verifies that nothing overflowed.  On overflow
-    // the call is redone below on the exact path (and the capacities are re-learned).
+    // ---- speculative-capacity forward: no count/scan passes and no mid-pipeline bubble ----
+    // The tile instances go straight into fixed-capacity sub-buckets sized from the previous forward of this shape;
+    // a one-CTA kernel right after preprocess checks that nothing overflowed, and the host reads its verdict only
+    // after the tile sort and the compositor have been enqueued behind it.  On overflow the results are discarded
+    // and the call is redone below on the exact path (which re-learns the capacities).
     const bool speculate = ctx->spec.sub_cap > 0 && ctx->spec.V == c.V && ctx->spec.ntiles == c.ntiles && n > 0 &&
                            !(cfg->tuning & (GS_TUNE_FORCE_RADIX_BINNING | GS_TUNE_NO_SPECULATION));
     if (speculate) {

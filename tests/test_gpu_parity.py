@@ -239,6 +239,16 @@ def test_binning_paths_agree_bit_for_bit():
     assert st_got["speculative"] == 0 and torch.equal(got, ref)
     again, st_again = _render_with_tuning(dense, dev, 0)       # capacities re-learned from the exact pass
     assert st_again["speculative"] == 1 and torch.equal(again, ref)
+    # every Gaussian twice (identical depth, different colour): the radix tile sort (depth bits only) meets ties in
+    # every tile and must hand those tiles to the 64-bit merge sort -- index order decides, as in the oracle
+    twin = make_scene(30000, 1, 64, 96, seed=9)
+    for name in ("means", "covariances", "opacities", "scales", "rotations"):
+        setattr(twin, name, torch.cat([getattr(twin, name)] * 2))
+    twin.harmonics = torch.cat([twin.harmonics, twin.harmonics.flip(1)])
+    tw, st_tw = _render_with_tuning(twin, dev, 0)
+    tw_slow, _ = _render_with_tuning(twin, dev, GS_TUNE_FORCE_RADIX_BINNING)
+    assert st_tw["max_tile_list"] > 2048 and torch.equal(tw, tw_slow)
+    check_image(tw[0], oracle_view(twin, 0), max_fragile_frac=1.0)   # every pixel sees equal depths: all "fragile"
     # 40k Gaussians squeezed into the centre of a 32x32 image: > 8192 entries in one tile
     huge = make_scene(40000, 1, 32, 32, seed=8)
     huge.means[:, :2] *= 0.05
