@@ -14,6 +14,7 @@
 namespace {
 
 constexpr int PRE_THREADS = 128;
+constexpr int EMIT_BATCH = 4;  // cursor atomics in flight per thread
 
 struct PreSmem {
     ViewCam cams[GS_CAM_CHUNK];
@@ -180,6 +181,24 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
         if (bulk) mbar_wait(&sm->bar, 0);
     }
 
+    // appends whose cursor value is still on its way back from L2 (see the emission below)
+    bool pend_ok[EMIT_BATCH];
+    uint32_t pend_slot[EMIT_BATCH], pend_pos[EMIT_BATCH];
+    uint64_t pend_key = 0;
+#pragma unroll
+    for (int k = 0; k < EMIT_BATCH; k++) {
+        pend_ok[k] = false;
+        pend_slot[k] = pend_pos[k] = 0;
+    }
+    auto flush_pending = [&]() {
+#pragma unroll
+        for (int k = 0; k < EMIT_BATCH; k++) {
+            if (pend_ok[k] && pend_pos[k] < emit.sub_cap)
+                emit.bucket[(size_t)pend_slot[k] * emit.sub_cap + pend_pos[k]] = pend_key;
+            pend_ok[k] = false;
+        }
+    };
+
     for (int v0 = 0; v0 < c.VPS; v0 += GS_CAM_CHUNK) {
         const int nv = min(GS_CAM_CHUNK, c.VPS - v0);
         __syncthreads();
@@ -202,25 +221,48 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
             // Hand this Gaussian to every (view, tile) list it joins.  Exact path: count it (RED.ADD, no return;
             // k_emit_buckets appends it later, once the offsets are known).  Speculative path: append it now to the
             // tile's fixed-capacity sub-bucket; an entry beyond the capacity is dropped and the overflow is detected
-            // from the cursor by k_tile_sort_spec (the call is then redone on the exact path).  Sub-bucket
+            // from the cursor by k_spec_check (the call is then redone on the exact path).  Sub-bucket
             // i % BIN_SUB, one counter per 32-byte sector -- see gs_binning.cu.  (With very many (view, tile) buckets the
             // fused appends of all views thrash L2; gs_forward then passes counters = NULL and emits per view instead.)
-            const uint64_t key = ((uint64_t)__float_as_uint(sp.r2.y) << 32) | (uint32_t)i;
-            if (emit.counters)
-            for (int ty = sp.rect.y; ty < sp.rect.w; ty++)
-                for (int tx = sp.rect.x; tx < sp.rect.z; tx++)
-                    if (gs_tile_reached(sp.r0, sp.r1, sp.r2, tx, ty)) {
-                        const size_t slot = ((size_t)v * c.ntiles + ty * c.gx + tx) * BIN_SUB + (i & (BIN_SUB - 1));
-                        if (emit.bucket) {
-                            const uint32_t pos = atomicAdd(&emit.counters[slot * BIN_PAD], 1u);
-                            if (pos < emit.sub_cap) emit.bucket[slot * emit.sub_cap + pos] = key;
-                        } else {
-                            atomicAdd(&emit.counters[slot * BIN_PAD], 1u);
+            if (emit.counters) {
+                const int w = sp.rect.z - sp.rect.x, nt = w * (sp.rect.w - sp.rect.y);
+                const uint32_t tbase = (uint32_t)v * (uint32_t)c.ntiles;
+                if (emit.bucket) {
+                    // The cursor atomics return the slot to write, an L2 round trip each (42 % of this kernel's stall
+                    // samples when the store followed its atomic directly).  Candidates go EMIT_BATCH at a time,
+                    // all their atomics in flight together, and the dependent stores are deferred until the next batch
+                    // is about to be issued -- normally one whole view of arithmetic later.
+                    for (int t0 = 0; t0 < nt; t0 += EMIT_BATCH) {
+                        bool ok[EMIT_BATCH];
+                        uint32_t slot[EMIT_BATCH];
+#pragma unroll
+                        for (int k = 0; k < EMIT_BATCH; k++) {
+                            const int t = t0 + k, ty = sp.rect.y + t / w, tx = sp.rect.x + t - (t / w) * w;
+                            ok[k] = t < nt && gs_tile_reached(sp.r0, sp.r1, sp.r2, tx, ty);
+                            slot[k] = (tbase + (uint32_t)(ty * c.gx + tx)) * BIN_SUB + ((uint32_t)i & (BIN_SUB - 1));
+                        }
+                        flush_pending();
+                        pend_key = ((uint64_t)__float_as_uint(sp.r2.y) << 32) | (uint32_t)i;
+#pragma unroll
+                        for (int k = 0; k < EMIT_BATCH; k++) {
+                            pend_ok[k] = ok[k];
+                            pend_slot[k] = slot[k];
+                            if (ok[k]) pend_pos[k] = atomicAdd(&emit.counters[(size_t)slot[k] * BIN_PAD], 1u);
                         }
                     }
+                } else {
+                    for (int t = 0; t < nt; t++) {
+                        const int ty = sp.rect.y + t / w, tx = sp.rect.x + t - (t / w) * w;
+                        if (gs_tile_reached(sp.r0, sp.r1, sp.r2, tx, ty))
+                            atomicAdd(&emit.counters[(size_t)((tbase + (uint32_t)(ty * c.gx + tx)) * BIN_SUB +
+                                                              ((uint32_t)i & (BIN_SUB - 1))) * BIN_PAD], 1u);
+                    }
+                }
+            }
             meta[o] = (uint8_t)sp.meta;
         }
     }
+    flush_pending();
 }
 
 __global__ void k_mark_visible(const DevCfg c, const float *__restrict__ means3D, uint8_t *__restrict__ present) {
