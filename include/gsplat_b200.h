@@ -187,6 +187,64 @@ GS_API int64_t gs_psnr_scratch_floats(int32_t batch, int64_t n);
 GS_API int gs_psnr(const float *ground_truth, const float *predicted, int32_t batch, int64_t n, float *scratch, float *out,
             void *stream);
 
+/*
+ * Fused Gaussian adapter: the per-Gaussian arithmetic of GaussianAdapter.forward,
+ * /root/reference/src/model/encoder/common/gaussian_adapter.py:48-98, for V cameras x R Gaussians each.  The
+ * per-camera quantities are computed by the caller with ordinary (differentiable) tensor code:
+ *   kinv       = intrinsics.inverse()                                   (geometry/projection.py:88-90)
+ *   multiplier = get_scale_multiplier(intrinsics, pixel_size)           (gaussian_adapter.py:100-111)
+ *   sh_rotation= block-diagonal Wigner-D of c2w[:3,:3] per degree       (misc/sh_rotation.py:10-36), NULL = identity
+ * Harmonics are written in the rasterizer's [d_sh][xyz] order (the reference's (xyz, d_sh) tensor is the transposed
+ * VIEW of it), so the relayout copy of decoder/cuda_splatting.py:75 disappears.  Opacities pass through untouched
+ * and are not an argument.
+ */
+typedef struct GsAdapterConfig {
+    int32_t V;          /* cameras (leading batch dims of extrinsics, flattened) */
+    int32_t R;          /* Gaussians per camera */
+    int32_t d_sh;       /* SH coefficients per channel, (sh_degree + 1)^2 <= 25 */
+    int32_t reserved_;
+    float scale_min;    /* GaussianAdapterCfg.gaussian_scale_min */
+    float scale_max;    /* GaussianAdapterCfg.gaussian_scale_max */
+    float eps;          /* forward(..., eps=1e-8) */
+    float reserved2_;
+    const float *c2w;         /* device [V,16] extrinsics, row-major */
+    const float *kinv;        /* device [V,9] */
+    const float *multiplier;  /* device [V] */
+    const float *sh_rotation; /* device [V,d_sh,d_sh] or NULL */
+    const float *sh_mask;     /* device [d_sh] (gaussian_adapter.py:39-46) */
+} GsAdapterConfig;
+
+typedef struct GsAdapterInputs {
+    const float *coordinates;   /* device [V,R,2] */
+    const float *depths;        /* device [V,R] */
+    const float *raw_gaussians; /* device [V,R,7+3*d_sh]: scales 3 | quaternion xyzw 4 | sh (xyz, d_sh) */
+} GsAdapterInputs;
+
+typedef struct GsAdapterOutputs { /* the fields of the reference's Gaussians dataclass (gaussian_adapter.py:13-20) */
+    float *means;       /* device [V,R,3] */
+    float *covariances; /* device [V,R,3,3] */
+    float *harmonics;   /* device [V,R,d_sh,3] */
+    float *scales;      /* device [V,R,3] */
+    float *rotations;   /* device [V,R,4] */
+} GsAdapterOutputs;
+
+typedef struct GsAdapterOutGrads { /* incoming gradients, same shapes as GsAdapterOutputs; NULL = zero */
+    const float *means, *covariances, *harmonics, *scales, *rotations;
+} GsAdapterOutGrads;
+
+typedef struct GsAdapterInGrads { /* any pointer may be NULL */
+    float *coordinates;   /* device [V,R,2] */
+    float *depths;        /* device [V,R] */
+    float *raw_gaussians; /* device [V,R,7+3*d_sh] */
+    float *c2w;           /* device [V,16]: through the means only (rotation is detached elsewhere, gaussian_adapter.py:81) */
+    float *kinv;          /* device [V,9] */
+    float *multiplier;    /* device [V] */
+} GsAdapterInGrads;
+
+GS_API int gs_adapter_forward(const GsAdapterConfig *cfg, const GsAdapterInputs *in, const GsAdapterOutputs *out, void *stream);
+GS_API int gs_adapter_backward(const GsAdapterConfig *cfg, const GsAdapterInputs *in, const GsAdapterOutGrads *gout,
+                        const GsAdapterInGrads *gin, void *stream);
+
 /* Per-stage device timings (ms) of the last forward/backward when profiling is enabled; CUDA events on `stream`. */
 enum { GS_STAGE_PREPROCESS = 0,      /* k_preprocess (incl. tile counting) */
        GS_STAGE_BIN_SCAN = 1,        /* k_tile_scan + the forward's one host read-back */

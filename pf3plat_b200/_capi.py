@@ -61,6 +61,32 @@ class GsStats(Structure):
 
 
 # every symbol include/gsplat_b200.h declares: name -> (restype, argtypes)
+class GsAdapterConfig(Structure):
+    _fields_ = [("V", c_int32), ("R", c_int32), ("d_sh", c_int32), ("reserved_", c_int32),
+                ("scale_min", c_float), ("scale_max", c_float), ("eps", c_float), ("reserved2_", c_float),
+                ("c2w", c_void_p), ("kinv", c_void_p), ("multiplier", c_void_p), ("sh_rotation", c_void_p),
+                ("sh_mask", c_void_p)]
+
+
+class GsAdapterInputs(Structure):
+    _fields_ = [("coordinates", c_void_p), ("depths", c_void_p), ("raw_gaussians", c_void_p)]
+
+
+class GsAdapterOutputs(Structure):
+    _fields_ = [("means", c_void_p), ("covariances", c_void_p), ("harmonics", c_void_p), ("scales", c_void_p),
+                ("rotations", c_void_p)]
+
+
+class GsAdapterOutGrads(Structure):
+    _fields_ = [("means", c_void_p), ("covariances", c_void_p), ("harmonics", c_void_p), ("scales", c_void_p),
+                ("rotations", c_void_p)]
+
+
+class GsAdapterInGrads(Structure):
+    _fields_ = [("coordinates", c_void_p), ("depths", c_void_p), ("raw_gaussians", c_void_p), ("c2w", c_void_p),
+                ("kinv", c_void_p), ("multiplier", c_void_p)]
+
+
 SYMBOLS = {
     "gs_abi_version": (c_int, []),
     "gs_last_error": (c_char_p, []),
@@ -77,6 +103,9 @@ SYMBOLS = {
     "gs_get_stage_ms": (c_int, [c_void_p, POINTER(c_float)]),
     "gs_psnr_scratch_floats": (c_int64, [c_int32, c_int64]),
     "gs_psnr": (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
+    "gs_adapter_forward": (c_int, [POINTER(GsAdapterConfig), POINTER(GsAdapterInputs), POINTER(GsAdapterOutputs), c_void_p]),
+    "gs_adapter_backward": (c_int, [POINTER(GsAdapterConfig), POINTER(GsAdapterInputs), POINTER(GsAdapterOutGrads),
+                                    POINTER(GsAdapterInGrads), c_void_p]),
 }
 
 
