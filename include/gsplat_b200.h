@@ -188,6 +188,17 @@ GS_API int gs_psnr(const float *ground_truth, const float *predicted, int32_t ba
             void *stream);
 
 /*
+ * SSIM per image = compute_ssim of /root/reference/src/evaluation/metrics.py:38-54, i.e. skimage's
+ * structural_similarity(win_size=11, gaussian_weights=True, channel_axis=0, data_range=1.0) -- on the device instead
+ * of a per-image round trip through the CPU.  Device pointers: ground_truth, predicted [batch, channels, height,
+ * width]; scratch [gs_ssim_scratch_floats(...)] floats, 8-byte aligned; out [batch].  Images smaller than 11 x 11
+ * are an error, as in skimage.  Deterministic (no atomics).
+ */
+GS_API int64_t gs_ssim_scratch_floats(int32_t batch, int32_t channels, int32_t height, int32_t width);
+GS_API int gs_ssim(const float *ground_truth, const float *predicted, int32_t batch, int32_t channels, int32_t height,
+            int32_t width, float *scratch, float *out, void *stream);
+
+/*
  * Fused Gaussian adapter: the per-Gaussian arithmetic of GaussianAdapter.forward,
  * /root/reference/src/model/encoder/common/gaussian_adapter.py:48-98, for V cameras x R Gaussians each.  The
  * per-camera quantities are computed by the caller with ordinary (differentiable) tensor code:

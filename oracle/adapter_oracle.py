@@ -77,7 +77,7 @@ def adapter_forward(extrinsics, intrinsics, coordinates, depths, opacities, raw_
     scales = scales * depths[..., None] * multiplier[..., None]
     rotations = rotations / (rotations.norm(dim=-1, keepdim=True) + eps)
     sh = sh.reshape(*sh.shape[:-1], 3, d_sh)
-    sh = sh.broadcast_to((*opacities.shape, 3, d_sh)) * sh_mask(sh_degree).to(dt)
+    sh = sh.broadcast_to((*opacities.shape, 3, d_sh)) * sh_mask(sh_degree).to(raw_gaussians)
     covariances = build_covariance(scales, rotations)
     c2w = extrinsics[..., :3, :3].detach()
     covariances = c2w @ covariances @ c2w.transpose(-1, -2)

@@ -1,6 +1,7 @@
 """GPU tests of the decoder-facing surface: the reference's call pattern (tests/ref_callsite.py restates
 cuda_splatting.py line by line) against the batched entry that replaces DecoderSplattingCUDA.forward
 (/root/reference/src/model/decoder/decoder_splatting_cuda.py:35-91)."""
+import numpy as np
 import pytest
 import torch
 
@@ -153,3 +154,27 @@ def test_psnr_matches_the_reference_formula():
         got = compute_psnr(gt.to(dev), pr.to(dev)).cpu().double()
         assert torch.allclose(got, ref, atol=1e-4, rtol=0), (got, ref)
         assert torch.equal(compute_psnr(gt.to(dev), pr.to(dev)).cpu().double(), got)     # deterministic
+
+
+@pytest.mark.parametrize("shape", [(4, 3, 256, 256), (2, 3, 37, 53), (1, 1, 11, 11), (3, 2, 43, 11)])
+def test_ssim_matches_the_restated_skimage_algorithm(shape):
+    """compute_ssim (gs_ssim) vs oracle/ssim_oracle.py (scipy's gaussian_filter, fp64).  Tolerance 2e-5 absolute: the
+    kernel filters in fp32 (skimage, on float32 input, does too)."""
+    from oracle import ssim_oracle
+    from pf3plat_b200.metrics import compute_ssim
+    g = torch.Generator().manual_seed(shape[-1])
+    gt = torch.rand(*shape, generator=g)
+    ys, xs = torch.meshgrid(torch.linspace(0, 6.28, shape[2]), torch.linspace(0, 6.28, shape[3]), indexing="ij")
+    gt = 0.5 * gt + 0.25 * (1 + torch.sin(3 * xs) * torch.cos(2 * ys))          # structure + noise
+    pred = (gt + 0.1 * torch.randn(*shape, generator=g)).clamp(0, 1)
+    pred[0] = gt[0]                                                              # identical pair -> exactly 1
+    got = compute_ssim(gt.cuda(), pred.cuda()).cpu().double().numpy()
+    want = ssim_oracle.compute_ssim(gt.numpy(), pred.numpy())
+    np.testing.assert_allclose(got, want, atol=2e-5, rtol=0)
+    assert abs(got[0] - 1.0) < 1e-6
+
+
+def test_ssim_rejects_images_smaller_than_the_window():
+    from pf3plat_b200.metrics import compute_ssim
+    with pytest.raises(ValueError, match="win_size exceeds image extent"):
+        compute_ssim(torch.zeros(1, 3, 10, 64, device="cuda"), torch.zeros(1, 3, 10, 64, device="cuda"))
