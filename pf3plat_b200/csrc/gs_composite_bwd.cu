@@ -8,31 +8,26 @@
 // B200 design.  Same CTA/warp/pixel mapping and the same ballot culling as the forward
 // (so both walk identical survivor sets).  Upstream issues 9 global float atomics per (pixel, Gaussian) pair;
 // here the 32 pixel lanes of a warp keep their 10 partial gradients for up to THREE Gaussians in registers
-// (30 values + 2 pads), a 31-shuffle butterfly transposes-and-reduces them so that lane L ends up holding the
+// (30 values), transpose them through a per-warp shared-memory buffer so that lane L ends up holding the
 // warp total of value L, and ONE red.global.add.f32 instruction with 30 distinct addresses retires them:
-// ~10 shuffles and one atomic instruction per Gaussian per warp instead of 45 shuffles or 288 atomics.
+// one atomic instruction per three Gaussians per warp instead of 288 atomics.  (The first version did the
+// transpose-reduce with a 31-shuffle register butterfly: 124 instructions per group against 71 now.)
 #include "gs_common.cuh"
 
 namespace {
 
 constexpr int CB_THREADS = 256;
 constexpr int CB_BATCH = 256;
-constexpr int CB_GROUP = 3;  // Gaussians reduced per butterfly (3 * GS_ACC_STRIDE = 30 <= 32)
+constexpr int CB_GROUP = 3;  // Gaussians reduced together (3 * GS_ACC_STRIDE = 30 values <= 32 lanes)
+constexpr int CB_RED_STRIDE = 36;  // floats per row of the transpose buffer: 16-byte aligned rows, conflict-free LDS.128
 
-// After this, lane L holds the sum over all 32 lanes of the caller's v[L].
-__device__ __forceinline__ float butterfly_reduce32(float (&v)[32], int lane) {
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
-        const bool upper = (lane & s) != 0;
-#pragma unroll
-        for (int i = 0; i < s; i++) {
-            const float send = upper ? v[i] : v[i + s];
-            const float keep = upper ? v[i + s] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-        }
-    }
-    return v[0];
-}
+// Shared memory of one CTA (dynamic: 61 KB).
+struct CbSmem {
+    float4 rec[2][CB_BATCH][3];                       // rec0 | rec1 | rec2, read as warp-wide broadcasts (double-buffered)
+    float red[CB_THREADS / 32][CB_GROUP * GS_ACC_STRIDE][CB_RED_STRIDE];  // per-warp transpose buffer of the reduction
+    uint32_t id[2][CB_BATCH];                         // Gaussian index of every staged entry (target of the atomics)
+    uint32_t max[CB_THREADS / 32];
+};
 
 // Per-pixel state of the reverse walk.
 struct PixState {
@@ -105,9 +100,11 @@ k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
                 const float *__restrict__ dL_ddepth, float *__restrict__ acc) {
     // double-buffered staging, as in the forward: the cp.async gathers of the next batch land in one buffer while the
     // warps walk the other
-    __shared__ float4 s_rec[2][CB_BATCH][3];  // rec0 | rec1 | rec2, read as warp-wide broadcasts
-    __shared__ uint32_t s_id[2][CB_BATCH];    // Gaussian index of every staged entry (target of the atomics)
-    __shared__ uint32_t s_max[CB_THREADS / 32];
+    extern __shared__ __align__(16) unsigned char cb_smem[];
+    CbSmem &sm = *reinterpret_cast<CbSmem *>(cb_smem);
+    auto &s_rec = sm.rec;
+    auto &s_id = sm.id;
+    auto &s_max = sm.max;
 
     const int v = blockIdx.y;
     const int tile = blockIdx.x;
@@ -120,6 +117,7 @@ k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
     const float bx0 = (float)bx, bx1 = (float)(bx + 7), by0 = (float)by, by1 = (float)(by + 3);
     const float half_w = 0.5f * (float)c.W, half_h = 0.5f * (float)c.H;
     const uint32_t stage_addr = smem_u32(&s_rec[0][0][0]);
+    constexpr uint32_t STAGE_BYTES = (uint32_t)sizeof(float4) * CB_BATCH * 3;
 
     const uint2 range = ranges[(size_t)v * c.ntiles + tile];
     const size_t rbase = (size_t)v * c.P;
@@ -184,7 +182,7 @@ k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
         id_next = load_id(k + 2);
         cp_async_wait<1>();  // this thread's part of batch k has landed ...
         __syncthreads();     // ... and so has everybody else's
-        const uint32_t rec_addr = stage_addr + (k & 1u) * (uint32_t)sizeof(s_rec[0]);
+        const uint32_t rec_addr = stage_addr + (k & 1u) * STAGE_BYTES;
         const uint32_t *sid = s_id[k & 1];
         if (lo >= warp_last) continue;  // nothing in this batch is below any of this warp's last contributors
         for (int chunk = (int)((nb - 1) & ~31u); chunk >= 0; chunk -= 32) {
@@ -197,7 +195,7 @@ k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
             }
             uint32_t mask = __ballot_sync(0xffffffffu, hit);
             while (mask) {
-                float gv[32];
+                float gv[CB_GROUP * GS_ACC_STRIDE];
                 uint32_t gid[CB_GROUP];
                 bool any_got = false;
 #pragma unroll
@@ -217,8 +215,25 @@ k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
                     }
                 }
                 if (!__any_sync(0xffffffffu, any_got)) continue;  // box hits that reached no pixel: nothing to add
-                gv[30] = gv[31] = 0.f;
-                const float total = butterfly_reduce32(gv, lane);
+                // Transpose-reduce through shared memory: every lane stores its 30 partial values down a column
+                // (row = value, column = lane; conflict-free), then lane r < 30 adds up row r with eight 16-byte loads.
+                // 30 STS + 8 LDS.128 + 31 FADD per group, against 31 SHFL + 62 FSEL + 31 FADD for a register butterfly.
+                float *red = &sm.red[warp][0][0];
+                __syncwarp();  // the previous group's row sums have been read
+#pragma unroll
+                for (int k = 0; k < CB_GROUP * GS_ACC_STRIDE; k++) red[k * CB_RED_STRIDE + lane] = gv[k];
+                __syncwarp();
+                float total = 0.f;
+                if (lane < CB_GROUP * GS_ACC_STRIDE) {
+                    const float4 *row = reinterpret_cast<const float4 *>(red + lane * CB_RED_STRIDE);
+                    float4 t = row[0];
+#pragma unroll
+                    for (int q = 1; q < 8; q++) {
+                        const float4 u = row[q];
+                        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+                    }
+                    total = (t.x + t.y) + (t.z + t.w);
+                }
                 const int slot = lane / GS_ACC_STRIDE, comp = lane - slot * GS_ACC_STRIDE;
                 uint32_t id = gid[0];
                 if (slot == 1) id = gid[1];
@@ -237,11 +252,14 @@ int launch_composite_bwd(const DevCfg &c, const GsSaved &s, const float *dL_dcol
                          float *grad_acc, cudaStream_t st) {
     if (c.V == 0 || c.ntiles == 0) return GS_OK;
     dim3 grid(c.ntiles, c.V);
+    const size_t smem = sizeof(CbSmem);
+    GS_CUDA_OK(cudaFuncSetAttribute(k_composite_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GS_CUDA_OK(cudaFuncSetAttribute(k_composite_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (c.flags & GS_FLAG_DEPTH)
-        k_composite_bwd<true><<<grid, CB_THREADS, 0, st>>>(c, s.rec0, s.rec1, s.rec2, s.point_list, s.ranges, s.final_T,
+        k_composite_bwd<true><<<grid, CB_THREADS, smem, st>>>(c, s.rec0, s.rec1, s.rec2, s.point_list, s.ranges, s.final_T,
                                                           s.n_contrib, dL_dcolor, dL_ddepth, grad_acc);
     else
-        k_composite_bwd<false><<<grid, CB_THREADS, 0, st>>>(c, s.rec0, s.rec1, s.rec2, s.point_list, s.ranges,
+        k_composite_bwd<false><<<grid, CB_THREADS, smem, st>>>(c, s.rec0, s.rec1, s.rec2, s.point_list, s.ranges,
                                                            s.final_T, s.n_contrib, dL_dcolor, dL_ddepth, grad_acc);
     GS_CUDA_OK(cudaGetLastError());
     return GS_OK;
