@@ -59,7 +59,8 @@ enum {
 enum {
     GS_TUNE_FORCE_RADIX_BINNING = 1u, /* use the device-wide radix-sort binning even when every tile list fits shared memory */
     GS_TUNE_NO_SPECULATION = 2u,      /* always size the tile buckets exactly (count + scan + emit passes, mid-call sync) */
-    GS_TUNE_SEPARATE_EMIT = 4u        /* speculative path: fill the buckets with k_emit_buckets even when they fit L2 */
+    GS_TUNE_SEPARATE_EMIT = 4u,       /* speculative path: fill the buckets with k_emit_buckets even when they fit L2 */
+    GS_TUNE_NO_STRATA = 8u            /* speculative path: never bin by depth stratum (whole-tile sorts only) */
 };
 
 /* GaussianRasterizationSettings (cuda_splatting.py:99-112), batched over views. */
@@ -136,7 +137,7 @@ typedef struct GsStats {
     int64_t scratch_bytes; /* bytes of grow-only scratch held by the context */
     int32_t kernel_launches; /* OUR kernels launched by the last forward (+ backward, if it followed); CUB's scan/sort launches are not counted */
     int32_t max_tile_list;   /* longest (view, tile) list of the last forward */
-    int32_t speculative;     /* 1 if the last forward ran on speculative bucket capacities (no count/scan/emit passes) */
+    int32_t speculative;     /* last forward: 0 exact capacities; 1 speculative capacities (no count/scan/emit passes); 2 the same, binned by depth stratum */
     int32_t reserved_;
 } GsStats;
 

@@ -90,7 +90,8 @@ k_tile_scan(int nvt, const uint32_t *__restrict__ counters, uint32_t *__restrict
 __global__ void k_emit_buckets(const DevCfg c, const float4 *__restrict__ rec0, const float4 *__restrict__ rec1,
                                const float4 *__restrict__ rec2, const ushort4 *__restrict__ rects,
                                const uint32_t *__restrict__ offsets, const uint32_t sub_cap,
-                               uint32_t *__restrict__ cursor, uint64_t *__restrict__ bucket) {
+                               const float *__restrict__ strata, uint32_t *__restrict__ cursor,
+                               uint64_t *__restrict__ bucket) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (size_t)c.V * c.P) return;
     const ushort4 r = rects[g];
@@ -100,7 +101,12 @@ __global__ void k_emit_buckets(const DevCfg c, const float4 *__restrict__ rec0, 
     const float4 q0 = rec0[g], q1 = rec1[g], q2 = rec2[g];
     const uint64_t key = ((uint64_t)__float_as_uint(q2.y) << 32) | i;
     const uint32_t tbase = v * (uint32_t)c.ntiles;
-    const uint32_t sub = i & (BIN_SUB - 1);
+    uint32_t sub = i & (BIN_SUB - 1);
+    if (strata) {  // sub-bucket = depth stratum of this view (same rule as k_preprocess)
+        sub = 0;
+#pragma unroll
+        for (int q = 0; q < BIN_SUB - 1; q++) sub += q2.y >= strata[(size_t)v * BIN_SUB + q] ? 1u : 0u;
+    }
     // The cursor atomics return values and the stores depend on them: handle the candidate tiles four at a time so
     // that several round trips to L2 are in flight per thread (the kernel is latency-bound: 16 % of issue slots busy).
     constexpr int BATCH = 4;
@@ -354,12 +360,12 @@ size_t bin_scratch_bytes(const DevCfg &c, int64_t D, bool fast) {
 }
 
 int bin_emit_fast(const DevCfg &c, int64_t D, const float4 *rec0, const float4 *rec1, const float4 *rec2,
-                  const ushort4 *rects, const uint32_t *offsets, uint32_t sub_cap, uint32_t *cursor, void *scratch,
-                  cudaStream_t st) {
+                  const ushort4 *rects, const uint32_t *offsets, uint32_t sub_cap, const float *strata, uint32_t *cursor,
+                  void *scratch, cudaStream_t st) {
     if (D <= 0) return GS_OK;
     GS_CUDA_OK(cudaMemsetAsync(cursor, 0, bin_counter_bytes(c), st));
     const size_t n = (size_t)c.V * c.P;
-    k_emit_buckets<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c, rec0, rec1, rec2, rects, offsets, sub_cap, cursor,
+    k_emit_buckets<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c, rec0, rec1, rec2, rects, offsets, sub_cap, strata, cursor,
                                                                  static_cast<uint64_t *>(scratch));
     GS_CUDA_OK(cudaGetLastError());
     return GS_OK;
@@ -387,6 +393,124 @@ int bin_spec_check(const DevCfg &c, uint32_t sub_cap, uint32_t tile_limit, const
                    cudaStream_t st) {
     const uint32_t cap = spec_sort_capacity(tile_limit);
     k_spec_check<<<1, SCAN_THREADS, 0, st>>>(c.V * c.ntiles, sub_cap, cap, cursor, info);
+    GS_CUDA_OK(cudaGetLastError());
+    return GS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Depth strata.  With sub-bucket = index % BIN_SUB a tile's list has to be sorted as a whole: one 1024-thread CTA,
+// ten merge rounds of CTA-wide barriers (0.246 ms on C2).  If instead the sub-bucket is chosen by DEPTH -- stratum q
+// holds the depths in [b_q, b_q+1) -- the tile's sorted list is the concatenation of its sorted sub-buckets, and each
+// is sorted on its own by a 128-thread CTA (seven rounds, four-warp barriers, eight times as many independent CTAs to
+// interleave): 0.170 ms.  The boundaries are per-view octiles of the depths of the previous exact-path call
+// (k_depth_hist / k_strata_from_hist); how well they balance only affects speed and capacity, never the result.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int STRATA_BINS = 2048;                       // 64 bins per octave of depth from 0.125 up
+constexpr uint32_t STRATA_BASE = 0x3E000000u >> 17;     // bit pattern of 0.125f, in bin units
+
+__device__ __forceinline__ int depth_bin(float d) {
+    const int b = (int)(__float_as_uint(d) >> 17) - (int)STRATA_BASE;  // monotone in d for positive floats
+    return min(max(b, 0), STRATA_BINS - 1);
+}
+
+// hist[v][bin] += number of candidate tiles of every binned Gaussian of view v (rect area: a proxy of its instances)
+__global__ void __launch_bounds__(256)
+k_depth_hist(const DevCfg c, const ushort4 *__restrict__ rects, const float4 *__restrict__ rec2, uint32_t *__restrict__ hist) {
+    __shared__ uint32_t h[STRATA_BINS];
+    const int v = blockIdx.y;
+    for (int k = threadIdx.x; k < STRATA_BINS; k += blockDim.x) h[k] = 0u;
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.P; i += gridDim.x * blockDim.x) {
+        const size_t o = (size_t)v * c.P + i;
+        const ushort4 r = rects[o];
+        const uint32_t area = (uint32_t)(r.z - r.x) * (uint32_t)(r.w - r.y);
+        if (area) atomicAdd(&h[depth_bin(rec2[o].y)], area);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < STRATA_BINS; k += blockDim.x)
+        if (h[k]) atomicAdd(&hist[(size_t)v * STRATA_BINS + k], h[k]);
+}
+
+// strata[v][q] = lower edge of the first bin above the (q+1)/BIN_SUB quantile, q < BIN_SUB - 1; last entry +inf.
+__global__ void __launch_bounds__(1024)
+k_strata_from_hist(const uint32_t *__restrict__ hist, float *__restrict__ strata) {
+    using Scan = cub::BlockScan<uint32_t, 1024>;
+    __shared__ typename Scan::TempStorage tmp;
+    const int v = blockIdx.x, t = threadIdx.x;
+    static_assert(STRATA_BINS == 2048, "two bins per thread");
+    const uint32_t a = hist[(size_t)v * STRATA_BINS + 2 * t], b = hist[(size_t)v * STRATA_BINS + 2 * t + 1];
+    uint32_t excl, total;
+    Scan(tmp).ExclusiveSum(a + b, excl, total);
+    if (t < BIN_SUB) strata[(size_t)v * BIN_SUB + t] = __int_as_float(0x7f800000);  // +inf: nothing reaches that stratum
+    __syncthreads();
+    if (total == 0) return;
+    const uint32_t cum[3] = {excl, excl + a, excl + a + b};  // mass below bin 2t, below bin 2t+1, below bin 2t+2
+#pragma unroll
+    for (int q = 1; q < BIN_SUB; q++) {
+        const uint64_t target = ((uint64_t)total * q + BIN_SUB - 1) / BIN_SUB;  // mass that should lie below boundary q
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+            if (cum[k] < target && cum[k + 1] >= target)  // bin 2t+k completes the quantile: the boundary is its upper edge
+                strata[(size_t)v * BIN_SUB + q - 1] = __uint_as_float((uint32_t)(2 * t + k + 1 + STRATA_BASE) << 17);
+    }
+}
+
+// One sub-bucket (= depth stratum) of one tile per CTA; it lands behind the tile's earlier strata.  CTA (vt, 0)
+// also writes the tile's range.
+template <int THREADS, int MAX_ITEMS>
+__global__ void __launch_bounds__(THREADS)
+k_stratum_sort(uint32_t sub_cap, const uint32_t *__restrict__ cursor, const uint64_t *__restrict__ bucket,
+               uint32_t *__restrict__ point_list, uint2 *__restrict__ ranges) {
+    extern __shared__ __align__(16) unsigned char ts_smem[];
+    const uint32_t vt = blockIdx.x / BIN_SUB, k = blockIdx.x % BIN_SUB;
+    uint32_t off = 0, n = 0, total = 0;
+#pragma unroll
+    for (int j = 0; j < BIN_SUB; j++) {
+        const uint32_t cnt = min(cursor[((size_t)vt * BIN_SUB + j) * BIN_PAD], sub_cap);  // clamped: an overflowed call is redone
+        if (j < (int)k) off += cnt;
+        if (j == (int)k) n = cnt;
+        total += cnt;
+    }
+    const uint32_t base = vt * BIN_SUB * sub_cap;
+    if (k == 0 && threadIdx.x == 0) ranges[vt] = make_uint2(base, base + total);
+    if (n == 0) return;
+    n = min(n, (uint32_t)(THREADS * MAX_ITEMS));
+    const uint64_t *src = bucket + ((size_t)vt * BIN_SUB + k) * sub_cap;
+    auto load = [src](uint32_t i) { return src[i]; };
+    uint32_t *dst = point_list + base + off;
+    static_assert(MAX_ITEMS == 16, "dispatch below");
+    if (n > THREADS * 8) sort_bucket_merge<THREADS, 16>(load, dst, n, ts_smem);
+    else if (n > THREADS * 4) sort_bucket_merge<THREADS, 8>(load, dst, n, ts_smem);
+    else if (n > THREADS * 2) sort_bucket_merge<THREADS, 4>(load, dst, n, ts_smem);
+    else if (n > THREADS) sort_bucket_merge<THREADS, 2>(load, dst, n, ts_smem);
+    else sort_bucket_merge<THREADS, 1>(load, dst, n, ts_smem);
+}
+
+int bin_sort_strata(const DevCfg &c, uint32_t sub_cap, const uint32_t *cursor, const void *bucket, uint32_t *point_list,
+                    uint2 *ranges, cudaStream_t st) {
+    // 128 threads: measured on C2 (sub-buckets of ~400 keys) 64 / 128 / 256 threads = 0.181 / 0.170 / 0.187 ms
+    constexpr int THREADS = 128, MAX_ITEMS = 16;
+    static_assert(THREADS * MAX_ITEMS == BIN_STRATUM_CAP, "capacity of a stratum");
+    if (sub_cap > BIN_STRATUM_CAP) return gs_set_error(GS_ERR_INVALID, "stratum capacity beyond the sort's");
+    const int nvt = c.V * c.ntiles;
+    const size_t smem = tile_sort_smem_bytes<THREADS, MAX_ITEMS>();
+    GS_CUDA_OK(cudaFuncSetAttribute(k_stratum_sort<THREADS, MAX_ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_stratum_sort<THREADS, MAX_ITEMS><<<nvt * BIN_SUB, THREADS, smem, st>>>(sub_cap, cursor, static_cast<const uint64_t *>(bucket),
+                                                                             point_list, ranges);
+    GS_CUDA_OK(cudaGetLastError());
+    return GS_OK;
+}
+
+size_t bin_strata_bytes(const DevCfg &c) { return (size_t)c.V * BIN_SUB * 4 + (size_t)c.V * STRATA_BINS * 4; }
+
+int bin_learn_strata(const DevCfg &c, const ushort4 *rects, const float4 *rec2, void *strata_buf, cudaStream_t st) {
+    float *strata = static_cast<float *>(strata_buf);
+    uint32_t *hist = reinterpret_cast<uint32_t *>(strata + (size_t)c.V * BIN_SUB);
+    GS_CUDA_OK(cudaMemsetAsync(hist, 0, (size_t)c.V * STRATA_BINS * 4, st));
+    const int bx = max(1, min(64, (c.P + 255) / 256));
+    k_depth_hist<<<dim3(bx, c.V), 256, 0, st>>>(c, rects, rec2, hist);
+    GS_CUDA_OK(cudaGetLastError());
+    k_strata_from_hist<<<c.V, 1024, 0, st>>>(hist, strata);
     GS_CUDA_OK(cudaGetLastError());
     return GS_OK;
 }

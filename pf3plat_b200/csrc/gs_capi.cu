@@ -46,6 +46,8 @@ struct GrowBuf {
     }
 };
 
+enum { STRATA_UNKNOWN = 0, STRATA_TRIAL = 1, STRATA_ON = 2, STRATA_OFF = 3 };
+
 struct GsContext {
     GrowBuf per_gaussian;  // rects | tile counts / offsets / cursors ; backward: accumulators
     GrowBuf sort;          // buckets (fast path) or radix-sort buffers (fallback)
@@ -57,7 +59,13 @@ struct GsContext {
         int V = 0, ntiles = 0;
         uint32_t sub_cap = 0;     // capacity of one of a tile's BIN_SUB sub-buckets
         uint32_t tile_limit = 0;  // list length the tile sort is launched for
+        // Depth strata (gs_binning.cu).  UNKNOWN: no boundaries for this shape yet.  TRIAL: boundaries learned by the
+        // last exact-path call, capacities still those of index % BIN_SUB sub-buckets -> the next speculative call
+        // tries strata with doubled capacities.  ON: strata with capacities learned from stratified counts.
+        // OFF: the trial overflowed (a tile whose depths crowd into one stratum): this shape stays on whole-tile sorts.
+        int strata_state = STRATA_UNKNOWN;
     } spec;
+    GrowBuf strata;        // [V][BIN_SUB] stratum boundaries + histogram scratch
     cudaEvent_t ev_pre = nullptr;   // "preprocess done" (speculative path: lets the radii copy start early)
     cudaEvent_t ev_info = nullptr;  // "binning verdict copied to the host"
     // gs_render_host: radii are final once the forward's mid-way sync has passed, so their copy to the host
@@ -169,6 +177,7 @@ void learn_capacities(GsContext *ctx, const DevCfg &c, uint32_t max_tile, uint32
         ctx->spec.sub_cap = 0;  // lists too long for the shared-memory sort (or offsets beyond 32 bits): exact path
         return;
     }
+    if (ctx->spec.V != c.V || ctx->spec.ntiles != c.ntiles) ctx->spec.strata_state = STRATA_UNKNOWN;
     ctx->spec.V = c.V;
     ctx->spec.ntiles = c.ntiles;
     ctx->spec.sub_cap = sub_cap;
@@ -207,6 +216,7 @@ extern "C" void gs_context_destroy(GsContext *ctx) {
     ctx->per_gaussian.release();
     ctx->sort.release();
     ctx->host_stage.release();
+    ctx->strata.release();
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->ev_pre) cudaEventDestroy(ctx->ev_pre);
     if (ctx->ev_info) cudaEventDestroy(ctx->ev_info);
@@ -321,7 +331,12 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     const bool speculate = ctx->spec.sub_cap > 0 && ctx->spec.V == c.V && ctx->spec.ntiles == c.ntiles && n > 0 &&
                            !(cfg->tuning & (GS_TUNE_FORCE_RADIX_BINNING | GS_TUNE_NO_SPECULATION));
     if (speculate) {
-        const uint32_t sub_cap = ctx->spec.sub_cap;
+        const bool strata = (ctx->spec.strata_state == STRATA_TRIAL || ctx->spec.strata_state == STRATA_ON) &&
+                            !(cfg->tuning & GS_TUNE_NO_STRATA) && ctx->strata.p != nullptr;
+        uint32_t sub_cap = ctx->spec.sub_cap;
+        if (strata && ctx->spec.strata_state == STRATA_TRIAL) sub_cap *= 2;  // capacities were learned unstratified
+        if (strata && sub_cap > BIN_STRATUM_CAP) sub_cap = BIN_STRATUM_CAP;
+        const float *strata_tab = strata ? static_cast<const float *>(ctx->strata.p) : nullptr;
         const size_t slots = nvt * BIN_SUB;
         rc = ctx->sort.reserve(slots * sub_cap * 8, 1.0);
         if (rc != GS_OK) return fail(rc);
@@ -338,13 +353,13 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
         const bool fused_emit = slots * sub_cap * 8 <= ((size_t)96 << 20) && !(cfg->tuning & GS_TUNE_SEPARATE_EMIT);
         {
             StageTimer t(ctx, GS_STAGE_PREPROCESS, st);
-            const PreEmit emit{fused_emit ? cursor : nullptr, static_cast<uint64_t *>(ctx->sort.p), sub_cap};
+            const PreEmit emit{fused_emit ? cursor : nullptr, static_cast<uint64_t *>(ctx->sort.p), sub_cap, strata_tab};
             rc = launch_preprocess(c, di, s->rec0, s->rec1, s->rec2, s->meta, out->radii, rects, emit, st);
             if (rc != GS_OK) return fail(rc);
         }
         if (!fused_emit) {
             StageTimer t(ctx, GS_STAGE_BIN_EMIT, st);
-            rc = bin_emit_fast(c, 1, s->rec0, s->rec1, s->rec2, rects, nullptr, sub_cap, cursor, ctx->sort.p, st);
+            rc = bin_emit_fast(c, 1, s->rec0, s->rec1, s->rec2, rects, nullptr, sub_cap, strata_tab, cursor, ctx->sort.p, st);
             if (rc != GS_OK) return fail(rc);
         }
         if (ctx->host_radii_dst && ctx->copy_stream) {  // radii leave for the host as soon as preprocess is done
@@ -368,14 +383,15 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
             StageTimer t(ctx, GS_STAGE_BIN_SCAN, st);
             // stored by the kernel straight into pinned host memory: an in-stream D2H copy would queue behind the
             // 16 MB radii copy of gs_render_host in the copy engine and hold up the kernels enqueued after it
-            rc = bin_spec_check(c, sub_cap, ctx->spec.tile_limit, cursor, ctx->d_word, st);
+            rc = bin_spec_check(c, sub_cap, strata ? 0xffffffffu : ctx->spec.tile_limit, cursor, ctx->d_word, st);
             if (rc != GS_OK) return fail(rc);
             e = cudaEventRecord(ctx->ev_info, st);
             if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "read back binning info", __FILE__, __LINE__));
         }
         {
             StageTimer t(ctx, GS_STAGE_BIN_SORT, st);
-            rc = bin_sort_spec(c, sub_cap, ctx->spec.tile_limit, cursor, ctx->sort.p, s->point_list, s->ranges, st);
+            if (strata) rc = bin_sort_strata(c, sub_cap, cursor, ctx->sort.p, s->point_list, s->ranges, st);
+            else rc = bin_sort_spec(c, sub_cap, ctx->spec.tile_limit, cursor, ctx->sort.p, s->point_list, s->ranges, st);
             if (rc != GS_OK) return fail(rc);
         }
         {
@@ -387,7 +403,20 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
         if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "cudaEventSynchronize", __FILE__, __LINE__));
         if (ctx->h_word[3] == 0) {
             const int64_t D = (int64_t)ctx->h_word[0];
-            learn_capacities(ctx, c, ctx->h_word[1], ctx->h_word[2]);
+            if (strata) {
+                // capacities for the next call from the stratified counts just measured; a stratum beyond the small
+                // sort's capacity sends this shape back to whole-tile sorts (via one exact-path call)
+                const uint32_t next = ctx->h_word[2] + ctx->h_word[2] * 3 / 10 + 16;
+                if (next > BIN_STRATUM_CAP) {
+                    ctx->spec.strata_state = STRATA_OFF;
+                    ctx->spec.sub_cap = 0;
+                } else {
+                    ctx->spec.strata_state = STRATA_ON;
+                    ctx->spec.sub_cap = next;
+                }
+            } else {
+                learn_capacities(ctx, c, ctx->h_word[1], ctx->h_word[2]);
+            }
             s->D = D;
             s->P = c.P; s->S = c.S; s->V = c.V; s->H = c.H; s->W = c.W;
             s->flags = c.flags;
@@ -398,13 +427,14 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
             ctx->stats.num_rendered = D;
             ctx->stats.num_visible = -1;
             ctx->stats.saved_bytes = (int64_t)(s->bytes + slots * sub_cap * 4);
-            ctx->stats.speculative = 1;
+            ctx->stats.speculative = strata ? 2 : 1;
             if (saved_out) *saved_out = s;
             else gs_saved_free(ctx, s, stream);
             return GS_OK;
         }
         // overflow: some sub-bucket or tile list outgrew its capacity.  Results are invalid; redo exactly.
         ctx->spec.sub_cap = 0;
+        if (strata) ctx->spec.strata_state = ctx->spec.strata_state == STRATA_TRIAL ? STRATA_OFF : STRATA_UNKNOWN;
         if (ctx->host_radii_dst && ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
         cudaFreeAsync(s->point_list, st);
         s->point_list = nullptr;
@@ -416,7 +446,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
         StageTimer t(ctx, GS_STAGE_PREPROCESS, st);
         cudaError_t e = cudaMemsetAsync(tile_counts, 0, bin_counter_bytes(c), st);
         if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "cudaMemsetAsync(tile_counts)", __FILE__, __LINE__));
-        const PreEmit emit{tile_counts, nullptr, 0};
+        const PreEmit emit{tile_counts, nullptr, 0, nullptr};  // exact path: sub-bucket = index % BIN_SUB
         rc = launch_preprocess(c, di, s->rec0, s->rec1, s->rec2, s->meta, out->radii, rects, emit, st);
         if (rc != GS_OK) return fail(rc);
         ctx->stats.kernel_launches += (c.P > 0);
@@ -454,7 +484,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     {
         StageTimer t(ctx, GS_STAGE_BIN_EMIT, st);
         if (fast)
-            rc = bin_emit_fast(c, D, s->rec0, s->rec1, s->rec2, rects, sub_offsets, 0, cursor, ctx->sort.p, st);
+            rc = bin_emit_fast(c, D, s->rec0, s->rec1, s->rec2, rects, sub_offsets, 0, nullptr, cursor, ctx->sort.p, st);
         else
             rc = bin_sort_fallback(c, D, s->rec0, s->rec1, s->rec2, rects, ctx->sort.p, ctx->sort.bytes, s->point_list,
                                    s->ranges, st);
@@ -473,6 +503,17 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
         rc = launch_composite_fwd(c, *s, out->color, out->depth, st);
         if (rc != GS_OK) return fail(rc);
         ctx->stats.kernel_launches += 1;
+    }
+
+    // Depth-stratum boundaries for the coming speculative calls, from this call's depths (off this call's critical
+    // path: queued behind the compositor).  STRATA_OFF is sticky for the shape.
+    if (fast && ctx->spec.sub_cap > 0 && ctx->spec.strata_state != STRATA_OFF && !(cfg->tuning & GS_TUNE_NO_STRATA) && n > 0) {
+        rc = ctx->strata.reserve(bin_strata_bytes(c), 1.0);
+        if (rc != GS_OK) return fail(rc);
+        rc = bin_learn_strata(c, rects, s->rec2, ctx->strata.p, st);
+        if (rc != GS_OK) return fail(rc);
+        ctx->spec.strata_state = STRATA_TRIAL;
+        ctx->stats.kernel_launches += 2;  // k_depth_hist, k_strata_from_hist
     }
 
     s->P = c.P; s->S = c.S; s->V = c.V; s->H = c.H; s->W = c.W;

@@ -63,6 +63,9 @@ struct PreEmit {
                           // (speculative path, fused emission); NULL = preprocess neither counts nor emits
     uint64_t *bucket;     // fused speculative emission only: fixed-capacity sub-buckets [V*tiles*BIN_SUB][sub_cap]
     uint32_t sub_cap;     // capacity of one sub-bucket (speculative path)
+    const float *strata;  // NULL: sub-bucket = index % BIN_SUB.  Else [V][BIN_SUB] ascending depth boundaries per view
+                          // (BIN_SUB - 1 used): sub-bucket = depth stratum, so that a tile's sorted list is the
+                          // concatenation of its independently sorted sub-buckets (gs_binning.cu, k_stratum_sort)
 };
 int launch_preprocess(const DevCfg &c, const DevInputs &in, float4 *rec0, float4 *rec1, float4 *rec2, uint8_t *meta,
                       int32_t *radii, ushort4 *rects, const PreEmit &emit, cudaStream_t st);
@@ -79,12 +82,18 @@ bool bin_fits_fast_path(uint32_t max_count);
 size_t bin_scratch_bytes(const DevCfg &c, int64_t D, bool fast);
 // offsets != NULL: exact-capacity buckets at offsets[slot]; offsets == NULL: fixed-capacity buckets at slot * sub_cap
 int bin_emit_fast(const DevCfg &c, int64_t D, const float4 *rec0, const float4 *rec1, const float4 *rec2,
-                  const ushort4 *rects, const uint32_t *offsets, uint32_t sub_cap, uint32_t *cursor, void *scratch,
-                  cudaStream_t st);
+                  const ushort4 *rects, const uint32_t *offsets, uint32_t sub_cap, const float *strata, uint32_t *cursor,
+                  void *scratch, cudaStream_t st);
 int bin_sort_fast(const DevCfg &c, uint32_t max_count, const uint32_t *tile_start, const uint32_t *tile_n,
                   const void *scratch, uint32_t *point_list, uint2 *ranges, cudaStream_t st);
 int bin_spec_check(const DevCfg &c, uint32_t sub_cap, uint32_t tile_limit, const uint32_t *cursor, uint32_t *info,
                    cudaStream_t st);
+int bin_sort_strata(const DevCfg &c, uint32_t sub_cap, const uint32_t *cursor, const void *bucket, uint32_t *point_list,
+                    uint2 *ranges, cudaStream_t st);
+// depth strata: per-view octiles of the depths of the binned Gaussians (weighted by their tile count), for the NEXT call
+size_t bin_strata_bytes(const DevCfg &c);          // strata table [V][BIN_SUB] floats + histogram scratch
+int bin_learn_strata(const DevCfg &c, const ushort4 *rects, const float4 *rec2, void *strata_buf, cudaStream_t st);
+constexpr uint32_t BIN_STRATUM_CAP = 2048;         // longest sub-bucket k_stratum_sort handles (128 threads x 16 keys)
 int bin_sort_spec(const DevCfg &c, uint32_t sub_cap, uint32_t tile_limit, const uint32_t *cursor, const void *bucket,
                   uint32_t *point_list, uint2 *ranges, cudaStream_t st);
 int bin_sort_fallback(const DevCfg &c, int64_t D, const float4 *rec0, const float4 *rec1, const float4 *rec2,

@@ -18,6 +18,7 @@ constexpr int EMIT_BATCH = 4;  // cursor atomics in flight per thread
 
 struct PreSmem {
     ViewCam cams[GS_CAM_CHUNK];
+    float strata[GS_CAM_CHUNK][BIN_SUB];  // depth-stratum boundaries of the staged views (PreEmit::strata)
     uint64_t bar;
 };
 constexpr int PRE_SMEM_HDR = (sizeof(PreSmem) + 127) / 128 * 128;
@@ -203,6 +204,9 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
         const int nv = min(GS_CAM_CHUNK, c.VPS - v0);
         __syncthreads();
         load_view_cams(c, scene * c.VPS + v0, nv, sm->cams);
+        if (emit.strata)
+            for (int t = tid; t < nv * BIN_SUB; t += PRE_THREADS)
+                sm->strata[t / BIN_SUB][t % BIN_SUB] = emit.strata[(size_t)(scene * c.VPS + v0) * BIN_SUB + t];
         __syncthreads();
         if (!active) continue;
         for (int vi = 0; vi < nv; vi++) {
@@ -227,6 +231,12 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
             if (emit.counters) {
                 const int w = sp.rect.z - sp.rect.x, nt = w * (sp.rect.w - sp.rect.y);
                 const uint32_t tbase = (uint32_t)v * (uint32_t)c.ntiles;
+                uint32_t sub = (uint32_t)i & (BIN_SUB - 1);
+                if (emit.strata) {
+                    sub = 0;
+#pragma unroll
+                    for (int q = 0; q < BIN_SUB - 1; q++) sub += sp.r2.y >= sm->strata[vi][q] ? 1u : 0u;
+                }
                 if (emit.bucket) {
                     // The cursor atomics return the slot to write, an L2 round trip each (42 % of this kernel's stall
                     // samples when the store followed its atomic directly).  Candidates go EMIT_BATCH at a time,
@@ -239,7 +249,7 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
                         for (int k = 0; k < EMIT_BATCH; k++) {
                             const int t = t0 + k, ty = sp.rect.y + t / w, tx = sp.rect.x + t - (t / w) * w;
                             ok[k] = t < nt && gs_tile_reached(sp.r0, sp.r1, sp.r2, tx, ty);
-                            slot[k] = (tbase + (uint32_t)(ty * c.gx + tx)) * BIN_SUB + ((uint32_t)i & (BIN_SUB - 1));
+                            slot[k] = (tbase + (uint32_t)(ty * c.gx + tx)) * BIN_SUB + sub;
                         }
                         flush_pending();
                         pend_key = ((uint64_t)__float_as_uint(sp.r2.y) << 32) | (uint32_t)i;
@@ -254,8 +264,7 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
                     for (int t = 0; t < nt; t++) {
                         const int ty = sp.rect.y + t / w, tx = sp.rect.x + t - (t / w) * w;
                         if (gs_tile_reached(sp.r0, sp.r1, sp.r2, tx, ty))
-                            atomicAdd(&emit.counters[(size_t)((tbase + (uint32_t)(ty * c.gx + tx)) * BIN_SUB +
-                                                              ((uint32_t)i & (BIN_SUB - 1))) * BIN_PAD], 1u);
+                            atomicAdd(&emit.counters[(size_t)((tbase + (uint32_t)(ty * c.gx + tx)) * BIN_SUB + sub) * BIN_PAD], 1u);
                     }
                 }
             }

@@ -45,6 +45,11 @@ def relerr(a, b):
     return np.abs(a - b.reshape(a.shape)).max() / max(np.abs(b).max(), 1e-30)
 
 
+def _last_stats(dev):
+    from pf3plat_b200.rasterizer import last_stats
+    return last_stats(dev)
+
+
 def render_batch(sc, dev, use_sh=True, with_depth=False, requires_grad=False, scale_rot=False):
     from pf3plat_b200.render import render_views
     d = sc.to(dev)
@@ -216,19 +221,24 @@ def _render_with_tuning(sc, dev, tuning):
 
 
 def test_binning_paths_agree_bit_for_bit():
-    """Exact-capacity buckets, speculative-capacity buckets (second call of a shape) and the device-wide radix-sort
-    fallback give the same lists, hence the same pixels; overflowing the learned capacities is detected and redone;
-    a scene whose densest tile exceeds the shared-memory sort capacity takes the radix fallback by itself."""
-    from pf3plat_b200._capi import GS_TUNE_FORCE_RADIX_BINNING, GS_TUNE_NO_SPECULATION, GS_TUNE_SEPARATE_EMIT
+    """Exact-capacity buckets, speculative-capacity buckets (later calls of a shape; whole-tile sorts or depth strata)
+    and the device-wide radix-sort fallback give the same lists, hence the same pixels; overflowing the learned
+    capacities is detected and redone; a scene whose densest tile exceeds the shared-memory sort capacity takes the
+    radix fallback by itself."""
+    from pf3plat_b200._capi import (GS_TUNE_FORCE_RADIX_BINNING, GS_TUNE_NO_SPECULATION, GS_TUNE_NO_STRATA,
+                                    GS_TUNE_SEPARATE_EMIT)
     dev = _dev()
     sc = make_scene(30000, 2, 64, 96, seed=7)
-    exact, st_exact = _render_with_tuning(sc, dev, GS_TUNE_NO_SPECULATION)
-    first, st_first = _render_with_tuning(sc, dev, 0)          # learns (or already has) the capacities
-    spec, st_spec = _render_with_tuning(sc, dev, 0)            # runs on them, appending from inside preprocess
+    exact, st_exact = _render_with_tuning(sc, dev, GS_TUNE_NO_SPECULATION)   # also learns capacities + depth strata
+    first, st_first = _render_with_tuning(sc, dev, 0)          # trial of the strata on doubled capacities
+    spec, st_spec = _render_with_tuning(sc, dev, 0)            # strata on their own learned capacities, fused appends
     spec2, st_spec2 = _render_with_tuning(sc, dev, GS_TUNE_SEPARATE_EMIT)   # same, buckets filled by k_emit_buckets
-    assert st_spec2["speculative"] == 1 and torch.equal(exact, spec2)
+    assert st_first["speculative"] == 2 and st_spec2["speculative"] == 2 and torch.equal(exact, spec2)
+    whole, st_whole = _render_with_tuning(sc, dev, GS_TUNE_NO_STRATA | GS_TUNE_NO_SPECULATION)  # re-learn unstratified
+    whole, st_whole = _render_with_tuning(sc, dev, GS_TUNE_NO_STRATA)        # speculative, whole-tile sorts
+    assert st_whole["speculative"] == 1 and torch.equal(exact, whole)
     slow, st_slow = _render_with_tuning(sc, dev, GS_TUNE_FORCE_RADIX_BINNING)
-    assert st_exact["speculative"] == 0 and st_spec["speculative"] == 1 and st_slow["speculative"] == 0
+    assert st_exact["speculative"] == 0 and st_spec["speculative"] == 2 and st_slow["speculative"] == 0
     assert st_exact["num_rendered"] == st_spec["num_rendered"] == st_slow["num_rendered"]
     assert st_exact["max_tile_list"] == st_spec["max_tile_list"] <= 8192
     assert torch.equal(exact, spec) and torch.equal(exact, slow) and torch.equal(exact, first)
@@ -238,7 +248,7 @@ def test_binning_paths_agree_bit_for_bit():
     ref, _ = _render_with_tuning(dense, dev, GS_TUNE_NO_SPECULATION)
     assert st_got["speculative"] == 0 and torch.equal(got, ref)
     again, st_again = _render_with_tuning(dense, dev, 0)       # capacities re-learned from the exact pass
-    assert st_again["speculative"] == 1 and torch.equal(again, ref)
+    assert st_again["speculative"] >= 1 and torch.equal(again, ref)
     # every Gaussian twice (identical depth, different colour): the radix tile sort (depth bits only) meets ties in
     # every tile and must hand those tiles to the 64-bit merge sort -- index order decides, as in the oracle
     twin = make_scene(30000, 1, 64, 96, seed=9)
@@ -276,3 +286,12 @@ def test_pixel_aligned_pf3plat_shaped_cloud():
         dL = (2 * (orc.color - target[v].cpu().numpy()) / target.numel()).astype(np.float32)
         gm = gm + orc.backward(dL)["means3D"]
     assert relerr(leaves["means"].grad[0], gm) <= GRAD_TOL
+    # Depth strata on a cloud whose tiles each see a narrow depth range (a smooth surface): the per-view octiles do
+    # not balance such tiles.  Whatever the library decides (strata kept, or dropped for this shape after the trial),
+    # every call gives the same pixels.
+    states = []
+    for _ in range(5):
+        again, _ = render_batch(sc, dev)
+        states.append(_last_stats(dev)["speculative"])
+        assert torch.equal(again, color.detach())
+    assert states[-1] >= 1, states
