@@ -457,23 +457,43 @@ k_strata_from_hist(const uint32_t *__restrict__ hist, float *__restrict__ strata
 }
 
 // One sub-bucket (= depth stratum) of one tile per CTA; it lands behind the tile's earlier strata.  CTA (vt, 0)
-// also writes the tile's range.
+// also writes the tile's range and adds the tile to the call's verdict (what k_spec_check computes for the whole-tile
+// path): acc = [0] total instances, [1] longest tile list, [2] largest sub-counter, [3] overflow flag, [4] tiles
+// accounted for; the last tile to arrive publishes [0..3] to `info` (mapped pinned memory the host is waiting on).
 template <int THREADS, int MAX_ITEMS>
 __global__ void __launch_bounds__(THREADS)
-k_stratum_sort(uint32_t sub_cap, const uint32_t *__restrict__ cursor, const uint64_t *__restrict__ bucket,
-               uint32_t *__restrict__ point_list, uint2 *__restrict__ ranges) {
+k_stratum_sort(uint32_t nvt, uint32_t sub_cap, const uint32_t *__restrict__ cursor, const uint64_t *__restrict__ bucket,
+               uint32_t *__restrict__ point_list, uint2 *__restrict__ ranges, uint32_t *__restrict__ acc,
+               uint32_t *__restrict__ info) {
     extern __shared__ __align__(16) unsigned char ts_smem[];
     const uint32_t vt = blockIdx.x / BIN_SUB, k = blockIdx.x % BIN_SUB;
-    uint32_t off = 0, n = 0, total = 0;
+    uint32_t off = 0, n = 0, total = 0, raw_total = 0, raw_max = 0;
 #pragma unroll
     for (int j = 0; j < BIN_SUB; j++) {
-        const uint32_t cnt = min(cursor[((size_t)vt * BIN_SUB + j) * BIN_PAD], sub_cap);  // clamped: an overflowed call is redone
+        const uint32_t raw = cursor[((size_t)vt * BIN_SUB + j) * BIN_PAD];
+        const uint32_t cnt = min(raw, sub_cap);  // clamped: an overflowed call is redone
         if (j < (int)k) off += cnt;
         if (j == (int)k) n = cnt;
         total += cnt;
+        raw_total += raw;
+        raw_max = max(raw_max, raw);
     }
     const uint32_t base = vt * BIN_SUB * sub_cap;
-    if (k == 0 && threadIdx.x == 0) ranges[vt] = make_uint2(base, base + total);
+    if (k == 0 && threadIdx.x == 0) {
+        ranges[vt] = make_uint2(base, base + total);
+        atomicAdd(&acc[0], raw_total);
+        atomicMax(&acc[1], raw_total);
+        atomicMax(&acc[2], raw_max);
+        if (raw_max > sub_cap) atomicOr(&acc[3], 1u);
+        __threadfence();
+        if (atomicAdd(&acc[4], 1u) == nvt - 1) {  // every tile has been accounted for
+            __threadfence();
+            info[0] = atomicAdd(&acc[0], 0u);
+            info[1] = atomicAdd(&acc[1], 0u);
+            info[2] = atomicAdd(&acc[2], 0u);
+            info[3] = atomicAdd(&acc[3], 0u);  // the host reads them after an event recorded behind this kernel
+        }
+    }
     if (n == 0) return;
     n = min(n, (uint32_t)(THREADS * MAX_ITEMS));
     const uint64_t *src = bucket + ((size_t)vt * BIN_SUB + k) * sub_cap;
@@ -488,7 +508,7 @@ k_stratum_sort(uint32_t sub_cap, const uint32_t *__restrict__ cursor, const uint
 }
 
 int bin_sort_strata(const DevCfg &c, uint32_t sub_cap, const uint32_t *cursor, const void *bucket, uint32_t *point_list,
-                    uint2 *ranges, cudaStream_t st) {
+                    uint2 *ranges, uint32_t *acc, uint32_t *info, cudaStream_t st) {
     // 128 threads: measured on C2 (sub-buckets of ~400 keys) 64 / 128 / 256 threads = 0.181 / 0.170 / 0.187 ms
     constexpr int THREADS = 128, MAX_ITEMS = 16;
     static_assert(THREADS * MAX_ITEMS == BIN_STRATUM_CAP, "capacity of a stratum");
@@ -496,8 +516,9 @@ int bin_sort_strata(const DevCfg &c, uint32_t sub_cap, const uint32_t *cursor, c
     const int nvt = c.V * c.ntiles;
     const size_t smem = tile_sort_smem_bytes<THREADS, MAX_ITEMS>();
     GS_CUDA_OK(cudaFuncSetAttribute(k_stratum_sort<THREADS, MAX_ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_stratum_sort<THREADS, MAX_ITEMS><<<nvt * BIN_SUB, THREADS, smem, st>>>(sub_cap, cursor, static_cast<const uint64_t *>(bucket),
-                                                                             point_list, ranges);
+    k_stratum_sort<THREADS, MAX_ITEMS><<<nvt * BIN_SUB, THREADS, smem, st>>>((uint32_t)nvt, sub_cap, cursor,
+                                                                             static_cast<const uint64_t *>(bucket), point_list,
+                                                                             ranges, acc, info);
     GS_CUDA_OK(cudaGetLastError());
     return GS_OK;
 }

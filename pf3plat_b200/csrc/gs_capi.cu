@@ -283,10 +283,10 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     for (bool &v : ctx->ev_valid) v = false;
     ctx->stats.kernel_launches = 0;
 
-    // ---- per-call scratch: rects[n] | counters | cursors | sub-bucket offsets | tile_start | tile_n ----
+    // ---- per-call scratch: rects[n] | counters | cursors | verdict words | sub-bucket offsets | tile_start | tile_n ----
     const size_t nvt = (size_t)c.V * c.ntiles;
     const size_t ctr_bytes = align256(bin_counter_bytes(c));
-    const size_t pg_bytes = align256(n * 8) + 2 * ctr_bytes + align256(nvt * BIN_SUB * 4) + 2 * align256(nvt * 4);
+    const size_t pg_bytes = align256(n * 8) + 2 * ctr_bytes + 256 + align256(nvt * BIN_SUB * 4) + 2 * align256(nvt * 4);
     rc = ctx->per_gaussian.reserve(pg_bytes, 1.0);
     if (rc != GS_OK) return rc;
     unsigned char *pg = static_cast<unsigned char *>(ctx->per_gaussian.p);
@@ -296,6 +296,8 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     pg += ctr_bytes;
     uint32_t *cursor = reinterpret_cast<uint32_t *>(pg);
     pg += ctr_bytes;
+    uint32_t *verdict_acc = reinterpret_cast<uint32_t *>(pg);  // directly behind the cursors: one memset clears both
+    pg += 256;
     uint32_t *sub_offsets = reinterpret_cast<uint32_t *>(pg);
     pg += align256(nvt * BIN_SUB * 4);
     uint32_t *tile_start = reinterpret_cast<uint32_t *>(pg);
@@ -345,7 +347,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
             s->point_list = nullptr;
             return fail(gs_set_cuda_error(e, "cudaMallocAsync(point_list)", __FILE__, __LINE__));
         }
-        e = cudaMemsetAsync(cursor, 0, bin_counter_bytes(c), st);
+        e = cudaMemsetAsync(cursor, 0, ctr_bytes + 256, st);
         if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "cudaMemsetAsync(cursors)", __FILE__, __LINE__));
         // Appending from inside preprocess touches the buckets of ALL views at once; beyond L2 size those 8-byte
         // appends turn into partial-sector DRAM writes (measured on C4: 4.5 ms fused vs 2.4 + 1.7 ms), so big bucket
@@ -362,36 +364,50 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
             rc = bin_emit_fast(c, 1, s->rec0, s->rec1, s->rec2, rects, nullptr, sub_cap, strata_tab, cursor, ctx->sort.p, st);
             if (rc != GS_OK) return fail(rc);
         }
-        if (ctx->host_radii_dst && ctx->copy_stream) {  // radii leave for the host as soon as preprocess is done
-            if (!ctx->ev_pre) e = cudaEventCreateWithFlags(&ctx->ev_pre, cudaEventDisableTiming);
-            if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_pre, st);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_pre, 0);
-            if (e == cudaSuccess)
-                e = cudaMemcpyAsync(ctx->host_radii_dst, out->radii, ctx->host_radii_bytes, cudaMemcpyDeviceToHost,
-                                    ctx->copy_stream);
-            if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "early radii copy", __FILE__, __LINE__));
-        }
-        // The verdict (overflow flag, counts) follows from the cursors alone: one tiny kernel right after preprocess,
-        // its 16 bytes copied out and marked with an event.  The tile sort and the compositor are enqueued behind it
-        // BEFORE the host waits on that event, so the wait overlaps them and the caller gets control back (to
-        // enqueue its next call) while the GPU is still busy.
+        // gs_render_host: the radii leave for the host on the copy stream as soon as they are final -- after preprocess
+        // on the whole-tile path; after the sort on the stratified path, whose last CTA stores the verdict into host
+        // memory (a store that would otherwise sit behind the 16 MB of radii on the PCIe link: +0.18 ms measured)
+        auto start_radii_copy = [&]() -> cudaError_t {
+            if (!(ctx->host_radii_dst && ctx->copy_stream)) return cudaSuccess;
+            cudaError_t ee = cudaSuccess;
+            if (!ctx->ev_pre) ee = cudaEventCreateWithFlags(&ctx->ev_pre, cudaEventDisableTiming);
+            if (ee == cudaSuccess) ee = cudaEventRecord(ctx->ev_pre, st);
+            if (ee == cudaSuccess) ee = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_pre, 0);
+            if (ee == cudaSuccess)
+                ee = cudaMemcpyAsync(ctx->host_radii_dst, out->radii, ctx->host_radii_bytes, cudaMemcpyDeviceToHost,
+                                     ctx->copy_stream);
+            return ee;
+        };
+        if (!strata && (e = start_radii_copy()) != cudaSuccess)
+            return fail(gs_set_cuda_error(e, "early radii copy", __FILE__, __LINE__));
+        // The verdict (overflow flag, counts) follows from the cursors alone.  Whole-tile path: one tiny kernel right
+        // after preprocess; stratified path: the sort's CTAs add it up themselves and the last one publishes it.  Either
+        // way it is stored straight into mapped pinned memory (an in-stream D2H copy would queue behind the 16 MB
+        // radii copy of gs_render_host in the copy engine) and marked with an event, and the remaining kernels are
+        // enqueued BEFORE the host waits on that event: the caller gets control back (to enqueue its next call) while
+        // the GPU is still busy.
         if (!ctx->ev_info) {
             e = cudaEventCreateWithFlags(&ctx->ev_info, cudaEventDisableTiming);
             if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "cudaEventCreate", __FILE__, __LINE__));
         }
-        {
+        if (!strata) {
             StageTimer t(ctx, GS_STAGE_BIN_SCAN, st);
-            // stored by the kernel straight into pinned host memory: an in-stream D2H copy would queue behind the
-            // 16 MB radii copy of gs_render_host in the copy engine and hold up the kernels enqueued after it
-            rc = bin_spec_check(c, sub_cap, strata ? 0xffffffffu : ctx->spec.tile_limit, cursor, ctx->d_word, st);
+            rc = bin_spec_check(c, sub_cap, ctx->spec.tile_limit, cursor, ctx->d_word, st);
             if (rc != GS_OK) return fail(rc);
             e = cudaEventRecord(ctx->ev_info, st);
             if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "read back binning info", __FILE__, __LINE__));
         }
         {
             StageTimer t(ctx, GS_STAGE_BIN_SORT, st);
-            if (strata) rc = bin_sort_strata(c, sub_cap, cursor, ctx->sort.p, s->point_list, s->ranges, st);
-            else rc = bin_sort_spec(c, sub_cap, ctx->spec.tile_limit, cursor, ctx->sort.p, s->point_list, s->ranges, st);
+            if (strata) {
+                rc = bin_sort_strata(c, sub_cap, cursor, ctx->sort.p, s->point_list, s->ranges, verdict_acc, ctx->d_word, st);
+                if (rc == GS_OK && (e = cudaEventRecord(ctx->ev_info, st)) != cudaSuccess)
+                    return fail(gs_set_cuda_error(e, "read back binning info", __FILE__, __LINE__));
+                if (rc == GS_OK && (e = start_radii_copy()) != cudaSuccess)
+                    return fail(gs_set_cuda_error(e, "early radii copy", __FILE__, __LINE__));
+            } else {
+                rc = bin_sort_spec(c, sub_cap, ctx->spec.tile_limit, cursor, ctx->sort.p, s->point_list, s->ranges, st);
+            }
             if (rc != GS_OK) return fail(rc);
         }
         {
@@ -422,7 +438,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
             s->flags = c.flags;
             s->has_sh = in->shs != nullptr;
             s->has_scales = in->scales != nullptr;
-            ctx->stats.kernel_launches = 4 + (fused_emit ? 0 : 1);  // k_preprocess, [k_emit_buckets], k_spec_check, k_tile_sort_spec, k_composite_fwd
+            ctx->stats.kernel_launches = (strata ? 3 : 4) + (fused_emit ? 0 : 1);  // k_preprocess, [k_emit_buckets], [k_spec_check,] tile sort, k_composite_fwd
             ctx->stats.max_tile_list = (int32_t)ctx->h_word[1];
             ctx->stats.num_rendered = D;
             ctx->stats.num_visible = -1;
