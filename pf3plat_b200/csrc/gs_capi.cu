@@ -73,6 +73,13 @@ struct GsContext {
     cudaStream_t copy_stream = nullptr;
     void *host_radii_dst = nullptr;
     size_t host_radii_bytes = 0;
+    // gs_render_host: the SH block arrives in feed_chunks pieces on the copy stream; piece k (Gaussians
+    // [feed_begin[k], feed_begin[k+1])) is complete once feed_ev[k] has fired, and preprocess runs piece by piece
+    // behind them, so all but the last piece of preprocess hides under the host-to-device transfer
+    static constexpr int FEED_MAX = 8;
+    int feed_chunks = 0;
+    int feed_begin[FEED_MAX + 1] = {};
+    cudaEvent_t feed_ev[FEED_MAX] = {};
     GsStats stats{};
     bool profiling = false;
     cudaEvent_t ev[GS_NUM_STAGES + 1][2]{};
@@ -218,6 +225,8 @@ extern "C" void gs_context_destroy(GsContext *ctx) {
     ctx->host_stage.release();
     ctx->strata.release();
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (cudaEvent_t ev : ctx->feed_ev)
+        if (ev) cudaEventDestroy(ev);
     if (ctx->ev_pre) cudaEventDestroy(ctx->ev_pre);
     if (ctx->ev_info) cudaEventDestroy(ctx->ev_info);
     if (ctx->h_word) cudaFreeHost(ctx->h_word);
@@ -356,7 +365,16 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
         {
             StageTimer t(ctx, GS_STAGE_PREPROCESS, st);
             const PreEmit emit{fused_emit ? cursor : nullptr, static_cast<uint64_t *>(ctx->sort.p), sub_cap, strata_tab};
-            rc = launch_preprocess(c, di, s->rec0, s->rec1, s->rec2, s->meta, out->radii, rects, emit, st);
+            if (ctx->feed_chunks > 0) {
+                for (int k = 0; k < ctx->feed_chunks && rc == GS_OK; k++) {
+                    e = cudaStreamWaitEvent(st, ctx->feed_ev[k], 0);
+                    if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "cudaStreamWaitEvent(feed)", __FILE__, __LINE__));
+                    rc = launch_preprocess(c, di, s->rec0, s->rec1, s->rec2, s->meta, out->radii, rects, emit, st,
+                                           ctx->feed_begin[k], ctx->feed_begin[k + 1]);
+                }
+            } else {
+                rc = launch_preprocess(c, di, s->rec0, s->rec1, s->rec2, s->meta, out->radii, rects, emit, st);
+            }
             if (rc != GS_OK) return fail(rc);
         }
         if (!fused_emit) {
@@ -463,6 +481,10 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
         cudaError_t e = cudaMemsetAsync(tile_counts, 0, bin_counter_bytes(c), st);
         if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "cudaMemsetAsync(tile_counts)", __FILE__, __LINE__));
         const PreEmit emit{tile_counts, nullptr, 0, nullptr};  // exact path: sub-bucket = index % BIN_SUB
+        for (int k = 0; k < ctx->feed_chunks; k++) {  // gs_render_host: every piece of the SH block must have landed
+            e = cudaStreamWaitEvent(st, ctx->feed_ev[k], 0);
+            if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "cudaStreamWaitEvent(feed)", __FILE__, __LINE__));
+        }
         rc = launch_preprocess(c, di, s->rec0, s->rec1, s->rec2, s->meta, out->radii, rects, emit, st);
         if (rc != GS_OK) return fail(rc);
         ctx->stats.kernel_launches += (c.P > 0);
@@ -629,16 +651,43 @@ extern "C" int gs_render_host(GsContext *ctx, const GsConfig *cfg, const GsInput
     // (A strided copy of only the SH bands the evaluator reads -- 192 of each 300-byte row -- was measured 2.3x
     // SLOWER end to end than the plain contiguous copy: cudaMemcpy2DAsync with 192-byte rows runs far below PCIe
     // rate.  Rows are copied whole.)
-    size_t off = 0;
+    if (!ctx->copy_stream) GS_CUDA_OK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    // The SH block is most of the bytes (C2: 150 of 170 MB).  A single scene's block goes over in pieces on the copy
+    // stream, each marked with an event, and gs_forward runs preprocess piece by piece behind them.
+    const size_t sh_row = (size_t)cfg->M * 12;
+    int pieces = 0;
+    if (in->shs && cfg->S == 1 && (size_t)cfg->P * sh_row >= ((size_t)16 << 20)) {
+        // measured on C2 inside one process (scripts/ab_e2e.py): 1 plain copy 3.965 ms, 2 pieces 3.863, 4: 3.820, 6: 3.799
+        const int req = (int)((cfg->tuning >> GS_TUNE_FEED_PIECES_SHIFT) & 0xFu);
+        pieces = req == 0 ? 6 : (req == 1 ? 0 : (req > GsContext::FEED_MAX ? GsContext::FEED_MAX : req));
+    }
+    // All copies of a pieced call go to the copy stream, everything else first and the SH pieces last (two streams
+    // feeding the same copy engine slowed each other down: +0.6 ms with the small arrays left on the launch stream).
+    size_t off = 0, sh_off = 0;
     for (const Item &it : items) {
         *it.d = nullptr;
         if (it.bytes) {
             *it.d = base + off;
-            GS_CUDA_OK(cudaMemcpyAsync(base + off, it.h, it.bytes, cudaMemcpyHostToDevice, st));
+            if (pieces && it.h == in->shs) sh_off = off;
+            else GS_CUDA_OK(cudaMemcpyAsync(base + off, it.h, it.bytes, cudaMemcpyHostToDevice, pieces ? ctx->copy_stream : st));
         }
         off += align256(it.bytes);
     }
-    if (!ctx->copy_stream) GS_CUDA_OK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (pieces) {
+        const int step = ((cfg->P + pieces - 1) / pieces + 511) / 512 * 512;  // whole CTAs, 16-byte aligned rows
+        int k = 0;
+        for (int g = 0; g < cfg->P; g += step, k++) {
+            const int g1 = g + step < cfg->P ? g + step : cfg->P;
+            if (!ctx->feed_ev[k]) GS_CUDA_OK(cudaEventCreateWithFlags(&ctx->feed_ev[k], cudaEventDisableTiming));
+            GS_CUDA_OK(cudaMemcpyAsync(base + sh_off + (size_t)g * sh_row, reinterpret_cast<const char *>(in->shs) + (size_t)g * sh_row,
+                                       (size_t)(g1 - g) * sh_row, cudaMemcpyHostToDevice, ctx->copy_stream));
+            GS_CUDA_OK(cudaEventRecord(ctx->feed_ev[k], ctx->copy_stream));
+            ctx->feed_begin[k] = g;
+            ctx->feed_begin[k + 1] = g1;
+        }
+        pieces = k;
+    }
+    ctx->feed_chunks = pieces;
     ctx->host_radii_dst = (out->radii && VP) ? out->radii : nullptr;
     ctx->host_radii_bytes = VP * 4;
     dout.color = reinterpret_cast<float *>(base + out_off);
@@ -647,6 +696,7 @@ extern "C" int gs_render_host(GsContext *ctx, const GsConfig *cfg, const GsInput
                                               : nullptr;
     rc = gs_forward(ctx, &dc, &din, &dout, nullptr, stream);
     ctx->host_radii_dst = nullptr;
+    ctx->feed_chunks = 0;
     if (rc != GS_OK) return rc;
     if (out->color) GS_CUDA_OK(cudaMemcpyAsync(out->color, dout.color, px * 12, cudaMemcpyDeviceToHost, st));
     if (out->depth && dout.depth) GS_CUDA_OK(cudaMemcpyAsync(out->depth, dout.depth, px * 4, cudaMemcpyDeviceToHost, st));

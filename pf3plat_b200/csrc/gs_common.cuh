@@ -68,7 +68,8 @@ struct PreEmit {
                           // concatenation of its independently sorted sub-buckets (gs_binning.cu, k_stratum_sort)
 };
 int launch_preprocess(const DevCfg &c, const DevInputs &in, float4 *rec0, float4 *rec1, float4 *rec2, uint8_t *meta,
-                      int32_t *radii, ushort4 *rects, const PreEmit &emit, cudaStream_t st);
+                      int32_t *radii, ushort4 *rects, const PreEmit &emit, cudaStream_t st, int g_begin = 0,
+                      int g_end = -1 /* = P */);
 int launch_mark_visible(const DevCfg &c, const float *means3D, uint8_t *present, cudaStream_t st);
 
 // binning (gs_binning.cu)

@@ -130,14 +130,14 @@ template <bool HAS_SH>
 __global__ void __launch_bounds__(PRE_THREADS)
 k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, float4 *__restrict__ rec1,
              float4 *__restrict__ rec2, uint8_t *__restrict__ meta, int32_t *__restrict__ radii,
-             ushort4 *__restrict__ rects, const PreEmit emit) {
+             ushort4 *__restrict__ rects, const PreEmit emit, const int g_begin, const int g_end) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PreSmem *sm = reinterpret_cast<PreSmem *>(smem_raw);
     float *sh_s = reinterpret_cast<float *>(smem_raw + PRE_SMEM_HDR);
 
     const int scene = blockIdx.y;
-    const int g0 = blockIdx.x * PRE_THREADS;
-    const int n = min(PRE_THREADS, c.P - g0);
+    const int g0 = g_begin + blockIdx.x * PRE_THREADS;  // this launch covers Gaussians [g_begin, g_end) of every scene
+    const int n = min(PRE_THREADS, g_end - g0);
     const int tid = threadIdx.x;
     const int i = g0 + tid;
     const bool active = tid < n;
@@ -290,15 +290,17 @@ __global__ void k_mark_visible(const DevCfg c, const float *__restrict__ means3D
 }  // namespace
 
 int launch_preprocess(const DevCfg &c, const DevInputs &in, float4 *rec0, float4 *rec1, float4 *rec2, uint8_t *meta,
-                      int32_t *radii, ushort4 *rects, const PreEmit &emit, cudaStream_t st) {
-    if (c.P == 0) return GS_OK;
-    dim3 grid((c.P + PRE_THREADS - 1) / PRE_THREADS, c.S);
+                      int32_t *radii, ushort4 *rects, const PreEmit &emit, cudaStream_t st, int g_begin, int g_end) {
+    if (g_end < 0) g_end = c.P;
+    if (g_end <= g_begin) return GS_OK;
+    dim3 grid((g_end - g_begin + PRE_THREADS - 1) / PRE_THREADS, c.S);
     if (in.shs) {
         size_t smem = PRE_SMEM_HDR + (size_t)PRE_THREADS * c.M * 12;
         GS_CUDA_OK(cudaFuncSetAttribute(k_preprocess<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_preprocess<true><<<grid, PRE_THREADS, smem, st>>>(c, in, rec0, rec1, rec2, meta, radii, rects, emit);
+        k_preprocess<true><<<grid, PRE_THREADS, smem, st>>>(c, in, rec0, rec1, rec2, meta, radii, rects, emit, g_begin, g_end);
     } else {
-        k_preprocess<false><<<grid, PRE_THREADS, PRE_SMEM_HDR, st>>>(c, in, rec0, rec1, rec2, meta, radii, rects, emit);
+        k_preprocess<false><<<grid, PRE_THREADS, PRE_SMEM_HDR, st>>>(c, in, rec0, rec1, rec2, meta, radii, rects, emit, g_begin,
+                                                                     g_end);
     }
     GS_CUDA_OK(cudaGetLastError());
     return GS_OK;

@@ -98,14 +98,17 @@ def test_orthographic_style_settings_with_tensor_tanfov():
     assert vis.dtype == torch.bool and vis.all()      # every synthetic Gaussian sits at z >= 1.5
 
 
-def test_host_buffer_entry_matches_device_entry():
-    """gs_render_host (C ABI with HOST pointers: the e2e path of bench.py) against the torch-facing device path."""
+@pytest.mark.parametrize("P", [20000, 70001])
+def test_host_buffer_entry_matches_device_entry(P):
+    """gs_render_host (C ABI with HOST pointers: the e2e path of bench.py) against the torch-facing device path.
+    70001 Gaussians: the SH block (21 MB) goes over in pieces with preprocess running piece by piece behind them;
+    called three times so that the exact, trial and stratified binning paths all see the pieced feed."""
     import ctypes
     from pf3plat_b200 import _capi, rasterizer
     from pf3plat_b200.cameras import make_view_batch
     from pf3plat_b200.rasterizer import BatchSettings, rasterize_batch
     dev = torch.device("cuda:0")
-    P, V, hw = 20000, 3, (64, 80)
+    V, hw = 3, (64, 80)
     sc = make_scene(P, V, *hw, seed=9)
     vb = make_view_batch(sc.extrinsics, sc.intrinsics, sc.near, sc.far)
     c = sc.covariances
@@ -127,14 +130,16 @@ def test_host_buffer_entry_matches_device_entry():
     depth = torch.empty(V, *hw)
     gout = _capi.GsOutputs(color=color.data_ptr(), radii=radii.data_ptr(), depth=depth.data_ptr())
     ctx = rasterizer.current_context(dev)
-    _capi.check(_capi.lib().gs_render_host(ctx, ctypes.byref(cfg), ctypes.byref(gin), ctypes.byref(gout),
-                                           torch.cuda.current_stream(dev).cuda_stream))
     d = {k: v.to(dev) for k, v in host.items()}
     bs = BatchSettings(image_height=hw[0], image_width=hw[1], viewmatrix=d["viewmatrix"], projmatrix=d["projmatrix"],
                        campos=d["campos"], bg=d["bg"], sh_degree=4, tanfov=d["tanfov"], with_depth=True)
     c2, r2, d2 = rasterize_batch(bs, d["means3D"][None], d["opacities"][None], shs=d["shs"][None],
                                  cov3D_precomp=d["cov3D_precomp"][None])
-    assert torch.equal(color, c2.cpu()) and torch.equal(radii, r2.cpu()) and torch.equal(depth, d2.cpu())
+    for _ in range(3):
+        color.zero_(); radii.zero_(); depth.zero_()
+        _capi.check(_capi.lib().gs_render_host(ctx, ctypes.byref(cfg), ctypes.byref(gin), ctypes.byref(gout),
+                                               torch.cuda.current_stream(dev).cuda_stream))
+        assert torch.equal(color, c2.cpu()) and torch.equal(radii, r2.cpu()) and torch.equal(depth, d2.cpu())
     # invalid argument combinations come back as the reference op's exceptions, not crashes
     bad = _capi.GsInputs(means3D=host["means3D"].data_ptr(), opacities=host["opacities"].data_ptr())
     with pytest.raises(ValueError, match="SHs or precomputed colors"):
