@@ -33,9 +33,33 @@ for (P, V, hw, tuning, depth, sr, sh) in [(3001, 3, (40, 56), 0, True, False, Tr
     else:
         c = sc.covariances
         kw["cov3D_precomp"] = torch.stack([c[:, 0, 0], c[:, 0, 1], c[:, 0, 2], c[:, 1, 1], c[:, 1, 2], c[:, 2, 2]], -1)[None].requires_grad_(True)
-    out = rasterize_batch(bs, means, opac, **kw)
-    loss = out[0].square().mean() + (out[2].mean() if depth else 0)
-    loss.backward()
-    torch.cuda.synchronize()
-    assert torch.isfinite(means.grad).all()
+    for rep in range(3):  # exact path (learns capacities + strata), strata trial, strata on their own capacities
+        means.grad = None
+        out = rasterize_batch(bs, means, opac, **kw)
+        loss = out[0].square().mean() + (out[2].mean() if depth else 0)
+        loss.backward()
+        torch.cuda.synchronize()
+        assert torch.isfinite(means.grad).all()
     print("ok", P, V, hw, tuning, depth, sr, sh)
+
+# ---- the rows next to the rasterizer: fused adapter (forward + backward), PSNR / SSIM ----
+from pf3plat_b200.adapter import GaussianAdapter, GaussianAdapterCfg  # noqa: E402
+from pf3plat_b200.metrics import compute_psnr, compute_ssim  # noqa: E402
+
+g = torch.Generator().manual_seed(0)
+for (b, v, r, deg) in [(1, 2, 300, 4), (2, 1, 129, 2), (1, 3, 1, 0)]:
+    d_in = 7 + 3 * (deg + 1) ** 2
+    ext = torch.eye(4).repeat(b, v, 1, 1).reshape(b, v, 1, 4, 4).to(dev)
+    intr = torch.tensor([[0.9, 0, 0.5], [0, 0.9, 0.5], [0, 0, 1.0]]).repeat(b, v, 1, 1).reshape(b, v, 1, 3, 3).to(dev)
+    raw = torch.randn(b, v, r, d_in, generator=g).to(dev).requires_grad_(True)
+    dep = (1 + torch.rand(b, v, r, generator=g)).to(dev).requires_grad_(True)
+    xy = torch.rand(b, v, r, 2, generator=g).to(dev)
+    opa = torch.rand(b, v, r, generator=g).to(dev)
+    ad = GaussianAdapter(GaussianAdapterCfg(0.5, 15.0, deg)).to(dev)
+    out = ad(ext, intr, xy, dep, opa, raw, (16, 16))
+    (out.means.sum() + out.covariances.sum() + out.harmonics.sum() + out.scales.sum()).backward()
+    torch.cuda.synchronize()
+    assert torch.isfinite(raw.grad).all() and torch.isfinite(dep.grad).all()
+    print("ok adapter", b, v, r, deg)
+a, bimg = torch.rand(2, 3, 45, 37, generator=g).to(dev), torch.rand(2, 3, 45, 37, generator=g).to(dev)
+print("ok metrics", compute_psnr(a, bimg).tolist(), compute_ssim(a, bimg).tolist())
