@@ -190,6 +190,17 @@ GS_API int gs_psnr(const float *ground_truth, const float *predicted, int32_t ba
             void *stream);
 
 /*
+ * Camera glue of render_cuda for all views of a call (/root/reference/src/model/decoder/cuda_splatting.py:64-87 with
+ * get_fov, /root/reference/src/geometry/projection.py:233-247, and get_projection_matrix, cuda_splatting.py:17-44).
+ * Device pointers.  In: extrinsics [B,16] camera-to-world (row-major), intrinsics [B,9] normalised, near/far [B];
+ * scale_invariant != 0 applies the 1/near rescale.  Out, in the layout GsConfig takes: viewmatrix, projmatrix [B,16]
+ * (transposed), campos [B,3], tanfov [B,2], view_scale [B].  No host synchronisation.
+ */
+GS_API int gs_view_batch(int32_t B, int32_t scale_invariant, const float *extrinsics, const float *intrinsics,
+                  const float *near_, const float *far_, float *viewmatrix, float *projmatrix, float *campos, float *tanfov,
+                  float *view_scale, void *stream);
+
+/*
  * SSIM per image = compute_ssim of /root/reference/src/evaluation/metrics.py:38-54, i.e. skimage's
  * structural_similarity(win_size=11, gaussian_weights=True, channel_axis=0, data_range=1.0) -- on the device instead
  * of a per-image round trip through the CPU.  Device pointers: ground_truth, predicted [batch, channels, height,

@@ -105,6 +105,7 @@ SYMBOLS = {
     "gs_get_stage_ms": (c_int, [c_void_p, POINTER(c_float)]),
     "gs_psnr_scratch_floats": (c_int64, [c_int32, c_int64]),
     "gs_psnr": (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
+    "gs_view_batch": (c_int, [c_int32, c_int32] + [c_void_p] * 10),
     "gs_ssim_scratch_floats": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
     "gs_ssim": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "gs_adapter_forward": (c_int, [POINTER(GsAdapterConfig), POINTER(GsAdapterInputs), POINTER(GsAdapterOutputs), c_void_p]),

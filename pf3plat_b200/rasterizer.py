@@ -184,6 +184,7 @@ class _RasterizeBatch(torch.autograd.Function):
             ctx.ins = ins            # contiguous fp32 inputs the backward kernels re-read
             ctx.cfg_keep = keep
             ctx.dims = (S, P, V, M, H, W)
+            ctx.want_means2D = means2D is not None and means2D.requires_grad
         ctx.mark_non_differentiable(radii)
         if bs.with_depth:
             return color, radii, depth
@@ -206,7 +207,7 @@ class _RasterizeBatch(torch.autograd.Function):
             og = GsOutGrads(_ptr(gcol), _ptr(gdep))
             e = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
             g = {
-                "dL_dmeans3D": e(S, P, 3), "dL_dmeans2D": e(V, P, 3),
+                "dL_dmeans3D": e(S, P, 3), "dL_dmeans2D": e(V, P, 3) if ctx.want_means2D else None,
                 "dL_dshs": e(S, P, M, 3) if ins["shs"] is not None else None,
                 "dL_dcolors": e(V, P, 3) if ins["colors_precomp"] is not None else None,
                 "dL_dopacities": e(*ins["opacities"].shape),
@@ -228,9 +229,8 @@ def rasterize_batch(bs: BatchSettings, means3D, opacities, shs=None, colors_prec
     (V,P,3); scales (S,P,3); rotations (S,P,4); cov3D_precomp (S,P,6); means2D (V,P,3) (gradient sink only).
     Returns (color (V,3,H,W), radii (V,P)[, depth (V,H,W)])."""
     _check_exclusive(shs, colors_precomp, scales, rotations, cov3D_precomp)
-    V = bs.viewmatrix.shape[0]
-    if means2D is None:
-        means2D = torch.zeros((V, means3D.shape[1], 3), dtype=torch.float32, device=means3D.device)
+    # means2D exists in the reference op only as a sink for the screen-space gradient (cuda_splatting.py:93-97); the
+    # batched entry neither allocates nor fills it unless the caller passes one
     return _RasterizeBatch.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, bs)
 
 

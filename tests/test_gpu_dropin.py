@@ -183,3 +183,30 @@ def test_ssim_rejects_images_smaller_than_the_window():
     from pf3plat_b200.metrics import compute_ssim
     with pytest.raises(ValueError, match="win_size exceeds image extent"):
         compute_ssim(torch.zeros(1, 3, 10, 64, device="cuda"), torch.zeros(1, 3, 10, 64, device="cuda"))
+
+
+@pytest.mark.parametrize("scale_invariant", [True, False])
+def test_camera_glue_kernel_matches_the_tensor_restatement(scale_invariant):
+    """gs_view_batch (one kernel, fp64 inside) against the plain-tensor restatement of cuda_splatting.py:64-87 that
+    tests/ref_callsite.py and the CPU path of make_view_batch use; general (non-rigid) extrinsics included, since the
+    reference calls a general .inverse().  Tolerance: fp32 rounding of the tensor path (~1e-6 relative)."""
+    from pf3plat_b200.cameras import make_view_batch
+    g = torch.Generator().manual_seed(4)
+    B = 37
+    ext = torch.eye(4).repeat(B, 1, 1)
+    ext[:, :3, :3] = torch.linalg.qr(torch.randn(B, 3, 3, generator=g))[0]
+    ext[:, :3, 3] = torch.randn(B, 3, generator=g)
+    ext[B // 2:, :3, :3] *= 1.0 + 0.1 * torch.rand(B - B // 2, 1, 1, generator=g)          # not orthonormal
+    intr = torch.eye(3).repeat(B, 1, 1)
+    intr[:, 0, 0] = 0.5 + torch.rand(B, generator=g)
+    intr[:, 1, 1] = 0.5 + torch.rand(B, generator=g)
+    intr[:, 0, 2] = 0.5 + 0.05 * torch.randn(B, generator=g)
+    intr[:, 1, 2] = 0.5 + 0.05 * torch.randn(B, generator=g)
+    near = 0.2 + torch.rand(B, generator=g)
+    far = 50 + 100 * torch.rand(B, generator=g)
+    cpu = make_view_batch(ext.double(), intr.double(), near.double(), far.double(), scale_invariant)   # fp64 truth
+    gpu = make_view_batch(ext.cuda(), intr.cuda(), near.cuda(), far.cuda(), scale_invariant)
+    for name in ("viewmatrix", "projmatrix", "campos", "tanfov", "scale"):
+        a, b = getattr(gpu, name).cpu().double(), getattr(cpu, name).double()
+        assert a.shape == b.shape, name
+        assert (a - b).abs().max() <= 2e-6 * max(1.0, float(b.abs().max())), (name, float((a - b).abs().max()))
