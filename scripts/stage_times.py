@@ -10,13 +10,17 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pf3plat_b200.cameras import make_view_batch  # noqa: E402
 from pf3plat_b200.rasterizer import BatchSettings, last_stats, rasterize_batch, set_profiling, stage_ms  # noqa: E402
-from pf3plat_b200.synthetic import make_scene, make_target  # noqa: E402
+from pf3plat_b200.synthetic import make_pixel_aligned_scene, make_scene, make_target  # noqa: E402
 
 P, V, HW = int(os.environ.get("GS_P", 500_000)), int(os.environ.get("GS_V", 8)), int(os.environ.get("GS_HW", 256))
 steps = int(os.environ.get("GS_STEPS", 20))
 tuning = int(os.environ.get("GS_TUNING", 0))
 dev = torch.device("cuda:0")
-sc = make_scene(P, V, HW, HW, seed=0).to(dev)
+if os.environ.get("GS_SCENE") == "aligned":   # PF3plat-shaped: one Gaussian per pixel of two context views (P is ignored)
+    sc = make_pixel_aligned_scene(HW, HW, V, seed=0).to(dev)
+    P = sc.means.shape[0]
+else:
+    sc = make_scene(P, V, HW, HW, seed=0).to(dev)
 vb = make_view_batch(sc.extrinsics, sc.intrinsics, sc.near, sc.far)
 bs = BatchSettings(image_height=HW, image_width=HW, viewmatrix=vb.viewmatrix, projmatrix=vb.projmatrix, campos=vb.campos,
                    bg=sc.background, sh_degree=4, tanfov=vb.tanfov, tuning=tuning)

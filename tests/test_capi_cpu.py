@@ -39,11 +39,13 @@ def test_library_loads_and_exports_every_declared_symbol(capi):
 
 
 def test_ctypes_struct_layouts_match_the_header(capi, tmp_path):
-    names = ["GsConfig", "GsInputs", "GsOutputs", "GsOutGrads", "GsInGrads", "GsStats"]
+    names = ["GsConfig", "GsInputs", "GsOutputs", "GsOutGrads", "GsInGrads", "GsStats", "GsAdapterConfig",
+             "GsAdapterInputs", "GsAdapterOutputs", "GsAdapterOutGrads", "GsAdapterInGrads"]
     prog = tmp_path / "sizes.c"
     prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "gsplat_b200.h"\nint main(void){'
                     + "".join(f'printf("%zu\\n", sizeof({n}));' for n in names)
                     + 'printf("%zu\\n", offsetof(GsConfig, viewmatrix));printf("%zu\\n", offsetof(GsConfig, tanfovx));'
+                    + 'printf("%zu\\n", offsetof(GsAdapterConfig, c2w));printf("%zu\\n", offsetof(GsAdapterConfig, eps));'
                     + "return 0;}")
     exe = tmp_path / "sizes"
     subprocess.run(["/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc", "-I", os.path.join(ROOT, "include"),
@@ -53,6 +55,8 @@ def test_ctypes_struct_layouts_match_the_header(capi, tmp_path):
         assert ctypes.sizeof(getattr(capi, n)) == int(sz), n
     assert capi.GsConfig.viewmatrix.offset == int(out[len(names)])
     assert capi.GsConfig.tanfovx.offset == int(out[len(names) + 1])
+    assert capi.GsAdapterConfig.c2w.offset == int(out[len(names) + 2])
+    assert capi.GsAdapterConfig.eps.offset == int(out[len(names) + 3])
 
 
 def test_null_arguments_are_rejected_without_a_device(capi):
@@ -63,6 +67,17 @@ def test_null_arguments_are_rejected_without_a_device(capi):
     assert L.gs_get_stats(None, None) == -1
     L.gs_saved_free(None, None, None)      # no-op
     L.gs_context_destroy(None)             # no-op
+    # the rows next to the rasterizer validate their arguments before touching the device too
+    assert L.gs_adapter_forward(None, None, None, None) == -1
+    assert L.gs_adapter_backward(None, None, None, None, None) == -1
+    assert L.gs_ssim(None, None, 1, 3, 32, 32, None, None, None) == -1
+    assert L.gs_psnr(None, None, 1, 10, None, None, None) == -1
+    assert L.gs_view_batch(1, 1, None, None, None, None, None, None, None, None, None, None) == -1
+    assert L.gs_view_batch(0, 1, None, None, None, None, None, None, None, None, None, None) == 0   # nothing to do
+    assert L.gs_ssim_scratch_floats(2, 3, 256, 256) == 2 * 2 * 3 * 64 and L.gs_ssim_scratch_floats(1, 3, 10, 64) == 0
+    bad = capi.GsAdapterConfig(V=1, R=1, d_sh=5)
+    assert L.gs_adapter_forward(ctypes.byref(bad), ctypes.byref(capi.GsAdapterInputs()), ctypes.byref(capi.GsAdapterOutputs()),
+                                None) == -1 and b"d_sh" in L.gs_last_error()
 
 
 def test_operator_surface_matches_the_reference_call_site():
