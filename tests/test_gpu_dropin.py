@@ -210,3 +210,22 @@ def test_camera_glue_kernel_matches_the_tensor_restatement(scale_invariant):
         a, b = getattr(gpu, name).cpu().double(), getattr(cpu, name).double()
         assert a.shape == b.shape, name
         assert (a - b).abs().max() <= 2e-6 * max(1.0, float(b.abs().max())), (name, float((a - b).abs().max()))
+
+
+def test_c5_chain_runs_end_to_end():
+    """scripts/c5_chain.py at a small size: stand-in encoder -> fused adapter -> batched decoder -> MSE -> backward ->
+    optimizer step -> PSNR/SSIM, all on the device; gradients reach the encoder's weights and are finite."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, C5_HW="48", C5_STEPS="2", C5_TARGETS="2")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "c5_chain.py")], env=env, capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["gradients_finite"] and line["n_gpus"] == 1 and line["ms_per_step"] > 0
+    assert 0.0 < line["loss_last"] < 1.0 and -1.0 <= line["ssim"] <= 1.0
