@@ -17,11 +17,12 @@
 namespace {
 
 constexpr int CB_THREADS = 256;
-constexpr int CB_BATCH = 256;
+constexpr int CB_BATCH_MAX = 256;
 constexpr int CB_GROUP = 3;  // Gaussians reduced together (3 * GS_ACC_STRIDE = 30 values <= 32 lanes)
 constexpr int CB_RED_STRIDE = 36;  // floats per row of the transpose buffer: 16-byte aligned rows, conflict-free LDS.128
 
 // Shared memory of one CTA (dynamic: 61 KB).
+template <int CB_BATCH>
 struct CbSmem {
     float4 rec[2][CB_BATCH][3];                       // rec0 | rec1 | rec2, read as warp-wide broadcasts (double-buffered)
     float red[CB_THREADS / 32][CB_GROUP * GS_ACC_STRIDE][CB_RED_STRIDE];  // per-warp transpose buffer of the reduction
@@ -91,8 +92,8 @@ __device__ __forceinline__ bool pixel_grad(PixState &ps, bool live, uint32_t rec
     return true;
 }
 
-template <bool DEPTH>
-__global__ void __launch_bounds__(CB_THREADS)
+template <bool DEPTH, int CB_BATCH, int MINB>
+__global__ void __launch_bounds__(CB_THREADS, MINB)
 k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *__restrict__ rec1,
                 const float4 *__restrict__ rec2, const uint32_t *__restrict__ point_list,
                 const uint2 *__restrict__ ranges, const float *__restrict__ final_T,
@@ -101,7 +102,7 @@ k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
     // double-buffered staging, as in the forward: the cp.async gathers of the next batch land in one buffer while the
     // warps walk the other
     extern __shared__ __align__(16) unsigned char cb_smem[];
-    CbSmem &sm = *reinterpret_cast<CbSmem *>(cb_smem);
+    CbSmem<CB_BATCH> &sm = *reinterpret_cast<CbSmem<CB_BATCH> *>(cb_smem);
     auto &s_rec = sm.rec;
     auto &s_id = sm.id;
     auto &s_max = sm.max;
@@ -252,15 +253,19 @@ int launch_composite_bwd(const DevCfg &c, const GsSaved &s, const float *dL_dcol
                          float *grad_acc, cudaStream_t st) {
     if (c.V == 0 || c.ntiles == 0) return GS_OK;
     dim3 grid(c.ntiles, c.V);
-    const size_t smem = sizeof(CbSmem);
-    GS_CUDA_OK(cudaFuncSetAttribute(k_composite_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GS_CUDA_OK(cudaFuncSetAttribute(k_composite_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (c.flags & GS_FLAG_DEPTH)
-        k_composite_bwd<true><<<grid, CB_THREADS, smem, st>>>(c, s.rec0, s.rec1, s.rec2, s.point_list, s.ranges, s.final_T,
-                                                          s.n_contrib, dL_dcolor, dL_ddepth, grad_acc);
-    else
-        k_composite_bwd<false><<<grid, CB_THREADS, smem, st>>>(c, s.rec0, s.rec1, s.rec2, s.point_list, s.ranges,
-                                                           s.final_T, s.n_contrib, dL_dcolor, dL_ddepth, grad_acc);
+    // Batch of 256 entries, registers unbounded (80 -> 3 CTAs/SM).  Measured on C2: a batch of 128 with registers
+    // bounded to 64 (4 CTAs/SM, 32 B of spills) 0.893 ms, a batch of 128 at 3 CTAs/SM 0.878 ms, this 0.859 ms -- the
+    // kernel is issue-bound, more resident warps do not help it.
+    constexpr int BATCH = CB_BATCH_MAX, MINB = 3;
+    const size_t smem = sizeof(CbSmem<BATCH>);
+    auto launch = [&](auto kern) -> int {
+        GS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, CB_THREADS, smem, st>>>(c, s.rec0, s.rec1, s.rec2, s.point_list, s.ranges, s.final_T, s.n_contrib,
+                                             dL_dcolor, dL_ddepth, grad_acc);
+        return GS_OK;
+    };
+    const int rc = (c.flags & GS_FLAG_DEPTH) ? launch(k_composite_bwd<true, BATCH, MINB>) : launch(k_composite_bwd<false, BATCH, MINB>);
+    if (rc != GS_OK) return rc;
     GS_CUDA_OK(cudaGetLastError());
     return GS_OK;
 }
