@@ -499,28 +499,38 @@ k_stratum_sort(uint32_t nvt, uint32_t sub_cap, const uint32_t *__restrict__ curs
     const uint64_t *src = bucket + ((size_t)vt * BIN_SUB + k) * sub_cap;
     auto load = [src](uint32_t i) { return src[i]; };
     uint32_t *dst = point_list + base + off;
-    static_assert(MAX_ITEMS == 16, "dispatch below");
-    if (n > THREADS * 8) sort_bucket_merge<THREADS, 16>(load, dst, n, ts_smem);
-    else if (n > THREADS * 4) sort_bucket_merge<THREADS, 8>(load, dst, n, ts_smem);
+    // cheapest instantiation that holds the stratum (the kernel itself is instantiated for the call's capacity)
+    if (MAX_ITEMS > 8 && n > THREADS * 8) sort_bucket_merge<THREADS, (MAX_ITEMS > 8 ? 16 : 1)>(load, dst, n, ts_smem);
+    else if (MAX_ITEMS > 4 && n > THREADS * 4) sort_bucket_merge<THREADS, (MAX_ITEMS > 4 ? 8 : 1)>(load, dst, n, ts_smem);
     else if (n > THREADS * 2) sort_bucket_merge<THREADS, 4>(load, dst, n, ts_smem);
     else if (n > THREADS) sort_bucket_merge<THREADS, 2>(load, dst, n, ts_smem);
     else sort_bucket_merge<THREADS, 1>(load, dst, n, ts_smem);
 }
 
-int bin_sort_strata(const DevCfg &c, uint32_t sub_cap, const uint32_t *cursor, const void *bucket, uint32_t *point_list,
-                    uint2 *ranges, uint32_t *acc, uint32_t *info, cudaStream_t st) {
-    // 128 threads: measured on C2 (sub-buckets of ~400 keys) 64 / 128 / 256 threads = 0.181 / 0.170 / 0.187 ms
-    constexpr int THREADS = 128, MAX_ITEMS = 16;
-    static_assert(THREADS * MAX_ITEMS == BIN_STRATUM_CAP, "capacity of a stratum");
-    if (sub_cap > BIN_STRATUM_CAP) return gs_set_error(GS_ERR_INVALID, "stratum capacity beyond the sort's");
-    const int nvt = c.V * c.ntiles;
+template <int THREADS, int MAX_ITEMS>
+int launch_stratum_sort(int nvt, uint32_t sub_cap, const uint32_t *cursor, const uint64_t *bucket, uint32_t *point_list,
+                        uint2 *ranges, uint32_t *acc, uint32_t *info, cudaStream_t st) {
     const size_t smem = tile_sort_smem_bytes<THREADS, MAX_ITEMS>();
     GS_CUDA_OK(cudaFuncSetAttribute(k_stratum_sort<THREADS, MAX_ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_stratum_sort<THREADS, MAX_ITEMS><<<nvt * BIN_SUB, THREADS, smem, st>>>((uint32_t)nvt, sub_cap, cursor,
-                                                                             static_cast<const uint64_t *>(bucket), point_list,
-                                                                             ranges, acc, info);
+    k_stratum_sort<THREADS, MAX_ITEMS><<<nvt * BIN_SUB, THREADS, smem, st>>>((uint32_t)nvt, sub_cap, cursor, bucket, point_list, ranges,
+                                                                             acc, info);
     GS_CUDA_OK(cudaGetLastError());
     return GS_OK;
+}
+
+int bin_sort_strata(const DevCfg &c, uint32_t sub_cap, const uint32_t *cursor, const void *bucket, uint32_t *point_list,
+                    uint2 *ranges, uint32_t *acc, uint32_t *info, cudaStream_t st) {
+    // 128 threads: measured on C2 (sub-buckets of ~400 keys) 64 / 128 / 256 threads = 0.181 / 0.170 / 0.187 ms.
+    // The kernel is instantiated for the call's capacity: the 4- and 8-keys-per-thread versions need fewer registers
+    // and less shared memory than the 16-key one, i.e. more resident CTAs for this latency-bound sort.
+    constexpr int THREADS = 128;
+    static_assert(THREADS * 16 == BIN_STRATUM_CAP, "capacity of a stratum");
+    if (sub_cap > BIN_STRATUM_CAP) return gs_set_error(GS_ERR_INVALID, "stratum capacity beyond the sort's");
+    const int nvt = c.V * c.ntiles;
+    const uint64_t *b = static_cast<const uint64_t *>(bucket);
+    if (sub_cap <= THREADS * 4) return launch_stratum_sort<THREADS, 4>(nvt, sub_cap, cursor, b, point_list, ranges, acc, info, st);
+    if (sub_cap <= THREADS * 8) return launch_stratum_sort<THREADS, 8>(nvt, sub_cap, cursor, b, point_list, ranges, acc, info, st);
+    return launch_stratum_sort<THREADS, 16>(nvt, sub_cap, cursor, b, point_list, ranges, acc, info, st);
 }
 
 size_t bin_strata_bytes(const DevCfg &c) { return (size_t)c.V * BIN_SUB * 4 + (size_t)c.V * STRATA_BINS * 4; }
