@@ -232,33 +232,22 @@ static void sh_to_rgb(int deg, int M, const real *mean, const real *campos, cons
     }
 }
 
-/* stable LSD radix sort of (key,value) on key bits [0,nbits) */
-static void radix_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t n, int nbits) {
-    if (n <= 1) return;
-    uint64_t *k2 = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)n);
-    uint32_t *v2 = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)n);
-    for (int shift = 0; shift < nbits; shift += 8) {
-        int64_t cnt[257];
-        memset(cnt, 0, sizeof(cnt));
-        for (int64_t i = 0; i < n; i++) cnt[((keys[i] >> shift) & 0xff) + 1]++;
-        for (int i = 0; i < 256; i++) cnt[i + 1] += cnt[i];
-        for (int64_t i = 0; i < n; i++) {
-            int64_t d = cnt[(keys[i] >> shift) & 0xff]++;
-            k2[d] = keys[i];
-            v2[d] = vals[i];
-        }
-        memcpy(keys, k2, sizeof(uint64_t) * (size_t)n);
-        memcpy(vals, v2, sizeof(uint32_t) * (size_t)n);
-    }
-    free(k2);
-    free(v2);
-}
-
 static real *dup_real(const real *src, size_t n) {
     if (!src) return NULL;
     real *d = (real *)malloc(sizeof(real) * (n ? n : 1));
-    memcpy(d, src, sizeof(real) * n);
+    const size_t chunk = (size_t)1 << 20; /* copied in parallel: the SH block alone is 150 MB in the C2 workload */
+    const int64_t nchunks = (int64_t)((n + chunk - 1) / chunk);
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < nchunks; c++) {
+        size_t lo = (size_t)c * chunk, len = n - lo < chunk ? n - lo : chunk;
+        memcpy(d + lo, src + lo, sizeof(real) * len);
+    }
     return d;
+}
+
+static int cmp_u64(const void *a, const void *b) {
+    uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+    return x < y ? -1 : (x > y ? 1 : 0);
 }
 
 void gso_free(gso_handle *h) {
@@ -404,44 +393,73 @@ gso_handle *gso_forward(const gso_params *pp, const real *means3D, const real *s
     }
     if (radii_out) memcpy(radii_out, h->radii, sizeof(int32_t) * (size_t)P);
 
-    /* ---- binning: duplicate with keys, stable sort, tile ranges ---- */
+    /* ---- binning: duplicate with keys, order by (tile, depth bits, index), tile ranges ----
+     * Upstream: ONE stable radix sort of (tile << 32 | depth bits) over all instances, emitted in index order.  The same
+     * order is produced here in a form that uses every host thread (bench.py times this code as the CPU baseline): a
+     * counting sort by tile over index-ordered chunks of Gaussians, then each tile's list sorted on its own by
+     * (depth bits, index) -- a total order, so the result does not depend on the number of threads. */
     int64_t D = 0, vis = 0;
-    int64_t *offs = (int64_t *)malloc(sizeof(int64_t) * ((size_t)P + 1));
-    for (int i = 0; i < P; i++) {
-        offs[i] = D;
-        D += h->tiles_touched[i];
-        vis += h->radii[i] > 0;
+    int nchunks = 1;
+#ifdef _OPENMP
+    nchunks = omp_get_max_threads();
+#endif
+    if (nchunks > P) nchunks = P > 0 ? P : 1;
+    int64_t *cnt = (int64_t *)calloc((size_t)nchunks * (size_t)ntiles + 1, sizeof(int64_t));
+#pragma omp parallel for schedule(static, 1)
+    for (int c = 0; c < nchunks; c++) {
+        int64_t *mine = cnt + (size_t)c * ntiles;
+        int lo = (int)((int64_t)P * c / nchunks), hi = (int)((int64_t)P * (c + 1) / nchunks);
+        for (int i = lo; i < hi; i++) {
+            if (h->radii[i] <= 0) continue;
+            const int32_t *rc = h->rect + 4 * (size_t)i;
+            for (int y = rc[1]; y < rc[3]; y++)
+                for (int x = rc[0]; x < rc[2]; x++) mine[y * gx + x]++;
+        }
+    }
+    for (int i = 0; i < P; i++) vis += h->radii[i] > 0;
+    h->ranges = (int64_t *)calloc((size_t)ntiles * 2, sizeof(int64_t));
+    for (int t = 0; t < ntiles; t++) { /* cnt[c][t] becomes chunk c's first slot in tile t */
+        int64_t start = D;
+        for (int c = 0; c < nchunks; c++) {
+            int64_t n = cnt[(size_t)c * ntiles + t];
+            cnt[(size_t)c * ntiles + t] = D;
+            D += n;
+        }
+        if (D > start) {
+            h->ranges[2 * t] = start;
+            h->ranges[2 * t + 1] = D;
+        }
     }
     h->D = D;
     h->vis = vis;
     h->keys = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(D + 1));
     h->point_list = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(D + 1));
-#pragma omp parallel for schedule(static)
-    for (int i = 0; i < P; i++) {
-        if (h->radii[i] <= 0) continue;
-        int64_t o = offs[i];
-        const int32_t *rc = h->rect + 4 * (size_t)i;
-        float df = (float)h->depths[i]; /* key always uses the fp32 bit pattern */
-        uint32_t dbits;
-        memcpy(&dbits, &df, 4);
-        for (int y = rc[1]; y < rc[3]; y++)
-            for (int x = rc[0]; x < rc[2]; x++) {
-                uint64_t key = ((uint64_t)(uint32_t)(y * gx + x) << 32) | dbits;
-                h->keys[o] = key;
-                h->point_list[o] = (uint32_t)i;
-                o++;
-            }
+    uint64_t *dk = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(D + 1)); /* (depth bits << 32 | index) per instance */
+#pragma omp parallel for schedule(static, 1)
+    for (int c = 0; c < nchunks; c++) {
+        int64_t *mine = cnt + (size_t)c * ntiles;
+        int lo = (int)((int64_t)P * c / nchunks), hi = (int)((int64_t)P * (c + 1) / nchunks);
+        for (int i = lo; i < hi; i++) {
+            if (h->radii[i] <= 0) continue;
+            const int32_t *rc = h->rect + 4 * (size_t)i;
+            float df = (float)h->depths[i]; /* key always uses the fp32 bit pattern */
+            uint32_t dbits;
+            memcpy(&dbits, &df, 4);
+            for (int y = rc[1]; y < rc[3]; y++)
+                for (int x = rc[0]; x < rc[2]; x++) dk[mine[y * gx + x]++] = ((uint64_t)dbits << 32) | (uint32_t)i;
+        }
     }
-    free(offs);
-    int tbits = 0;
-    while ((1 << tbits) < ntiles) tbits++;
-    radix_sort_pairs(h->keys, h->point_list, D, 32 + tbits + 1);
-    h->ranges = (int64_t *)calloc((size_t)ntiles * 2, sizeof(int64_t));
-    for (int64_t i = 0; i < D; i++) {
-        uint32_t t = (uint32_t)(h->keys[i] >> 32);
-        if (i == 0 || t != (uint32_t)(h->keys[i - 1] >> 32)) h->ranges[2 * t] = i;
-        if (i == D - 1 || t != (uint32_t)(h->keys[i + 1] >> 32)) h->ranges[2 * t + 1] = i + 1;
+    free(cnt);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int t = 0; t < ntiles; t++) {
+        int64_t r0 = h->ranges[2 * t], r1 = h->ranges[2 * t + 1];
+        if (r1 - r0 > 1) qsort(dk + r0, (size_t)(r1 - r0), sizeof(uint64_t), cmp_u64); /* keys are distinct */
+        for (int64_t k = r0; k < r1; k++) {
+            h->keys[k] = ((uint64_t)(uint32_t)t << 32) | (dk[k] >> 32);
+            h->point_list[k] = (uint32_t)dk[k];
+        }
     }
+    free(dk);
 
     /* ---- composite forward ---- */
     h->final_T = (real *)calloc((size_t)H * W, sizeof(real));
