@@ -152,3 +152,42 @@ def test_empty_cloud():
     r = OracleRender(st, means3D=np.zeros((0, 3)), opacities=np.zeros(0), colors_precomp=np.zeros((0, 3)),
                      cov3D_precomp=np.zeros((0, 6)))
     assert r.num_rendered == 0 and np.allclose(r.color[1], 0.25)
+
+
+def test_tile_lists_are_in_depth_then_index_order_for_any_thread_count():
+    """The binning's contract (Appendix A "Binning": stable sort of (tile | depth bits) over instances emitted in index
+    order): inside every tile range the (fp32 depth bits, Gaussian index) pairs strictly increase, every Gaussian
+    appears once per tile of its rect, and the lists do not depend on the number of OpenMP threads."""
+    from oracle import gs_oracle
+    from pf3plat_b200.synthetic import make_scene
+    from tests.util import view_args
+    sc = make_scene(20000, 2, 96, 80, seed=5)
+    # duplicate some Gaussians so that equal depths occur inside tiles
+    import torch
+    for name in ("means", "covariances", "opacities", "harmonics", "scales", "rotations"):
+        t = getattr(sc, name)
+        setattr(sc, name, torch.cat([t, t[:3000]]))
+    st, kw = view_args(sc, 1)
+    lists = []
+    prev = gs_oracle.set_threads(0)
+    try:
+        for threads in (1, 3, max(prev, 2)):
+            gs_oracle.set_threads(threads)
+            r = OracleRender(st, **kw)
+            pl, rg, tt = r.point_list, r.ranges, r.tiles_touched
+            depth_bits = r.depths.astype(np.float32).view(np.uint32).astype(np.uint64)
+            assert int(tt.sum()) == r.num_rendered == len(pl)
+            assert np.array_equal(np.bincount(pl, minlength=len(tt)), tt)
+            key = (depth_bits[pl] << np.uint64(32)) | pl.astype(np.uint64)
+            covered = 0
+            for a, b in rg:
+                if b > a:
+                    assert np.all(key[a + 1:b] > key[a:b - 1])
+                    covered += b - a
+            assert covered == len(pl)
+            lists.append((pl.copy(), rg.copy(), r.color.copy()))
+            r.close()
+    finally:
+        gs_oracle.set_threads(prev)
+    for pl, rg, col in lists[1:]:
+        assert np.array_equal(pl, lists[0][0]) and np.array_equal(rg, lists[0][1]) and np.array_equal(col, lists[0][2])
