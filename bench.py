@@ -96,6 +96,29 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
+def host_threads() -> int:
+    """CPU threads this process may really use: the affinity mask and a cgroup CPU quota (containers) both cap
+    os.cpu_count(); oversubscribing a quota with one OpenMP thread per visible CPU makes the CPU baseline slower."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    try:  # cgroup v2, then v1
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, -(-int(quota) // int(period))))
+    except (OSError, ValueError):
+        try:
+            quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota > 0 and period > 0:
+                n = min(n, max(1, -(-quota // period)))
+        except (OSError, ValueError):
+            pass
+    return max(1, n)
+
+
 def run_reference(args):
     """CPU arm: the oracle port on the host cores, one whole view of the workload per step."""
     import numpy as np
@@ -106,7 +129,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import gs_oracle
-    cores = gs_oracle.set_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1: ask for all cores
+    cores = gs_oracle.set_threads(host_threads())   # torchrun exports OMP_NUM_THREADS=1: ask for all usable cores
     sc = make_scene(P_GAUSS, VIEWS, HW, HW, seed=0)
     for _ in range(args.warmup):
         st, kw = view_args(sc, 0)
@@ -288,7 +311,7 @@ def main():
             from oracle import gs_oracle
             from oracle.gs_oracle import OracleRender
             from tests.util import view_args
-            cores = gs_oracle.set_threads(os.cpu_count() or 1)
+            cores = gs_oracle.set_threads(host_threads())
             # (1) in this process, untimed: the oracle's tile-instance count D of every view of this rank (the D of the
             #     algorithmic-bytes formulas) and the worst RGB difference of view 0
             Ds = []
