@@ -1,0 +1,111 @@
+"""Generates tests/golden/camera_glue.npz by running the REFERENCE's own render_cuda
+(/root/reference/src/model/decoder/cuda_splatting.py:47-127, imported unmodified from the read-only tree) against a
+RECORDING stand-in for `diff_gaussian_rasterization`: the stub rasterizer stores the GaussianRasterizationSettings it is
+handed for every view (viewmatrix, projmatrix, campos, tanfovx, tanfovy -- everything lines 64-112 compute) and returns
+blank images.  The fixture therefore pins pf3plat_b200.cameras.make_view_batch / gs_view_batch to the reference's own glue.
+Only runs in the build container (needs /root/reference).   Usage: python tests/golden/make_camera_golden.py"""
+import importlib.util
+import os
+import sys
+import types
+from typing import NamedTuple
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_ROOT = "/root/reference"
+RECORDED: list = []
+
+
+class _Settings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+class _Recorder:
+    def __init__(self, raster_settings):
+        self.s = raster_settings
+
+    def __call__(self, means3D, means2D, shs=None, colors_precomp=None, opacities=None, cov3D_precomp=None, **kw):
+        s = self.s
+        RECORDED.append(dict(viewmatrix=s.viewmatrix.detach().clone(), projmatrix=s.projmatrix.detach().clone(),
+                             campos=s.campos.detach().clone(), tanfov=torch.tensor([float(s.tanfovx), float(s.tanfovy)]),
+                             means=means3D.detach().clone(), cov6=cov3D_precomp.detach().clone()))
+        return torch.zeros(3, s.image_height, s.image_width), torch.zeros(means3D.shape[0], dtype=torch.int32)
+
+
+def load_reference_render_cuda():
+    stub = types.ModuleType("diff_gaussian_rasterization")
+    stub.GaussianRasterizationSettings = _Settings
+    stub.GaussianRasterizer = _Recorder
+    saved = sys.modules.get("diff_gaussian_rasterization")
+    sys.modules["diff_gaussian_rasterization"] = stub
+    try:
+        for name in ("src", "src.model", "src.model.decoder", "src.model.encoder", "src.model.encoder.costvolume", "src.geometry"):
+            m = types.ModuleType(name)
+            m.__path__ = [os.path.join(REF_ROOT, *name.split("."))]
+            sys.modules[name] = m
+        path = os.path.join(REF_ROOT, "src/model/decoder/cuda_splatting.py")
+        spec = importlib.util.spec_from_file_location("src.model.decoder.cuda_splatting", path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[spec.name] = mod
+        spec.loader.exec_module(mod)
+        return mod
+    finally:
+        if saved is not None:
+            sys.modules["diff_gaussian_rasterization"] = saved
+        else:
+            del sys.modules["diff_gaussian_rasterization"]
+
+
+def make_cameras(seed, B):
+    g = torch.Generator().manual_seed(seed)
+    ext = torch.eye(4).repeat(B, 1, 1)
+    ext[:, :3, :3] = torch.linalg.qr(torch.randn(B, 3, 3, generator=g))[0]
+    ext[:, :3, 3] = torch.randn(B, 3, generator=g)
+    intr = torch.eye(3).repeat(B, 1, 1)
+    intr[:, 0, 0] = 0.6 + 0.6 * torch.rand(B, generator=g)
+    intr[:, 1, 1] = 0.6 + 0.6 * torch.rand(B, generator=g)
+    intr[:, 0, 2] = 0.5 + 0.03 * torch.randn(B, generator=g)
+    intr[:, 1, 2] = 0.5 + 0.03 * torch.randn(B, generator=g)
+    near = 0.3 + torch.rand(B, generator=g)
+    far = 40 + 100 * torch.rand(B, generator=g)
+    return ext, intr, near, far
+
+
+def main():
+    mod = load_reference_render_cuda()
+    B, G = 9, 2
+    ext, intr, near, far = make_cameras(12, B)
+    g = torch.Generator().manual_seed(13)
+    means = torch.randn(B, G, 3, generator=g)
+    a = torch.randn(B, G, 3, 3, generator=g)
+    cov = a @ a.transpose(-1, -2)
+    sh = torch.randn(B, G, 3, 25, generator=g)
+    opac = torch.rand(B, G, generator=g)
+    arrays = dict(extrinsics=ext.numpy(), intrinsics=intr.numpy(), near=near.numpy(), far=far.numpy(),
+                  means=means.numpy(), covariances=cov.numpy())
+    for tag, si in (("si", True), ("raw", False)):
+        RECORDED.clear()
+        mod.render_cuda(ext, intr, near, far, (16, 24), torch.zeros(B, 3), means, cov, sh, opac, scale_invariant=si)
+        assert len(RECORDED) == B
+        for k in ("viewmatrix", "projmatrix", "campos", "tanfov", "means", "cov6"):
+            arrays[f"{tag}_{k}"] = torch.stack([r[k] for r in RECORDED]).numpy()
+    path = os.path.join(HERE, "camera_glue.npz")
+    np.savez_compressed(path, **arrays)
+    print({k: v.shape for k, v in arrays.items()}, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,54 @@
+"""Pins the camera glue (pf3plat_b200/cameras.py: the tensor path here, the gs_view_batch kernel in
+tests/test_gpu_dropin.py) to the REFERENCE's own render_cuda: tests/golden/camera_glue.npz holds the
+GaussianRasterizationSettings that /root/reference/src/model/decoder/cuda_splatting.py:64-112 handed to a recording
+rasterizer stub, view by view (tests/golden/make_camera_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from pf3plat_b200.cameras import make_view_batch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "camera_glue.npz")
+
+
+def check_against_golden(vb, z, tag, tol):
+    for name, got in (("viewmatrix", vb.viewmatrix), ("projmatrix", vb.projmatrix), ("campos", vb.campos),
+                      ("tanfov", vb.tanfov)):
+        want = z[f"{tag}_{name}"].astype(np.float64)
+        got = got.detach().cpu().double().numpy()
+        assert got.shape == want.shape, name
+        assert np.abs(got - want).max() <= tol * max(1.0, np.abs(want).max()), (tag, name, np.abs(got - want).max())
+    # the 1/near rescale the reference applies to the Gaussians (cuda_splatting.py:64-71) is what view_scale stands for
+    s = vb.scale.detach().cpu().double().numpy()
+    np.testing.assert_allclose(z["means"] * s[:, None, None], z[f"{tag}_means"], rtol=1e-6, atol=1e-7)
+    c = z["covariances"] * (s ** 2)[:, None, None, None]
+    cov6 = np.stack([c[..., 0, 0], c[..., 0, 1], c[..., 0, 2], c[..., 1, 1], c[..., 1, 2], c[..., 2, 2]], -1)
+    np.testing.assert_allclose(cov6, z[f"{tag}_cov6"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag,scale_invariant", [("si", True), ("raw", False)])
+def test_tensor_path_matches_what_the_reference_hands_its_rasterizer(tag, scale_invariant):
+    z = np.load(GOLDEN)
+    t = lambda k: torch.from_numpy(z[k])
+    vb = make_view_batch(t("extrinsics"), t("intrinsics"), t("near"), t("far"), scale_invariant)
+    check_against_golden(vb, z, tag, 2e-6)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/model/decoder/cuda_splatting.py"),
+                    reason="reference tree only exists in the build container")
+def test_fixture_is_what_the_reference_produces_today(tmp_path):
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); import make_camera_golden as m; "
+            "mod = m.load_reference_render_cuda(); ext, intr, near, far = m.make_cameras(12, 9); import torch; "
+            "m.RECORDED.clear(); g = torch.Generator().manual_seed(13); means = torch.randn(9, 2, 3, generator=g); "
+            "a = torch.randn(9, 2, 3, 3, generator=g); cov = a @ a.transpose(-1, -2); sh = torch.randn(9, 2, 3, 25, generator=g); "
+            "op = torch.rand(9, 2, generator=g); mod.render_cuda(ext, intr, near, far, (16, 24), torch.zeros(9, 3), means, cov, sh, op); "
+            "np.save(%r, torch.stack([r['projmatrix'] for r in m.RECORDED]).numpy())") % (os.path.join(here, "golden"),
+                                                                                           str(tmp_path / "p.npy"))
+    env = dict(os.environ, PYTHONPATH=os.path.dirname(here))
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
+    np.testing.assert_allclose(np.load(tmp_path / "p.npy"), np.load(GOLDEN)["si_projmatrix"], rtol=1e-6, atol=1e-7)

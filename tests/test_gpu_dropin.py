@@ -229,3 +229,14 @@ def test_c5_chain_runs_end_to_end():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["gradients_finite"] and line["n_gpus"] == 1 and line["ms_per_step"] > 0
     assert 0.0 < line["loss_last"] < 1.0 and -1.0 <= line["ssim"] <= 1.0
+
+
+@pytest.mark.parametrize("tag,scale_invariant", [("si", True), ("raw", False)])
+def test_camera_glue_kernel_matches_what_the_reference_hands_its_rasterizer(tag, scale_invariant):
+    """gs_view_batch against the settings the reference's own render_cuda produced (tests/golden/camera_glue.npz)."""
+    from pf3plat_b200.cameras import make_view_batch
+    from tests.test_camera_cpu import GOLDEN, check_against_golden
+    z = np.load(GOLDEN)
+    t = lambda k: torch.from_numpy(z[k]).cuda()
+    vb = make_view_batch(t("extrinsics"), t("intrinsics"), t("near"), t("far"), scale_invariant)
+    check_against_golden(vb, z, tag, 3e-6)
