@@ -41,7 +41,13 @@ class _Recorder:
         s = self.s
         RECORDED.append(dict(viewmatrix=s.viewmatrix.detach().clone(), projmatrix=s.projmatrix.detach().clone(),
                              campos=s.campos.detach().clone(), tanfov=torch.tensor([float(s.tanfovx), float(s.tanfovy)]),
-                             means=means3D.detach().clone(), cov6=cov3D_precomp.detach().clone()))
+                             means=means3D.detach().clone(), cov6=cov3D_precomp.detach().clone(),
+                             bg=s.bg.detach().clone().float(), opacities=opacities.detach().clone(),
+                             colors=(torch.zeros(0) if colors_precomp is None else colors_precomp.detach().clone()),
+                             shs=(torch.zeros(0) if shs is None else shs.detach().clone()),
+                             ints=torch.tensor([s.image_height, s.image_width, s.sh_degree, int(s.prefiltered), int(s.debug)]),
+                             scale_modifier=torch.tensor(float(s.scale_modifier)),
+                             means2D_is_zero_leaf=torch.tensor(int(bool((means2D == 0).all()) and means2D.requires_grad))))
         return torch.zeros(3, s.image_height, s.image_width), torch.zeros(means3D.shape[0], dtype=torch.int32)
 
 
@@ -102,6 +108,20 @@ def main():
         assert len(RECORDED) == B
         for k in ("viewmatrix", "projmatrix", "campos", "tanfov", "means", "cov6"):
             arrays[f"{tag}_{k}"] = torch.stack([r[k] for r in RECORDED]).numpy()
+    # the depth renders: what render_depth_cuda (:226-269) hands the op in each of its modes (fake colours, bg, flags)
+    for mode in ("depth", "disparity", "relative_disparity", "log"):
+        RECORDED.clear()
+        mod.render_depth_cuda(ext, intr, near, far, (16, 24), means.abs() + 0.5, cov, opac, mode=mode)
+        assert len(RECORDED) == B
+        for k in ("colors", "bg", "opacities", "ints", "scale_modifier", "means2D_is_zero_leaf"):
+            arrays[f"depth_{mode}_{k}"] = torch.stack([r[k] for r in RECORDED]).numpy()
+    # and the colour render's remaining arguments
+    RECORDED.clear()
+    mod.render_cuda(ext, intr, near, far, (16, 24), torch.rand(B, 3, generator=torch.Generator().manual_seed(14)), means, cov, sh, opac)
+    for k in ("shs", "bg", "opacities", "ints", "scale_modifier", "means2D_is_zero_leaf"):
+        arrays[f"color_{k}"] = torch.stack([r[k] for r in RECORDED]).numpy()
+    arrays["sh"] = sh.numpy()
+    arrays["opacities"] = opac.numpy()
     path = os.path.join(HERE, "camera_glue.npz")
     np.savez_compressed(path, **arrays)
     print({k: v.shape for k, v in arrays.items()}, os.path.getsize(path), "bytes")

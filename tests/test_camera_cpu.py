@@ -52,3 +52,43 @@ def test_fixture_is_what_the_reference_produces_today(tmp_path):
     env = dict(os.environ, PYTHONPATH=os.path.dirname(here))
     subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
     np.testing.assert_allclose(np.load(tmp_path / "p.npy"), np.load(GOLDEN)["si_projmatrix"], rtol=1e-6, atol=1e-7)
+
+
+def test_callsite_restatement_hands_the_op_what_the_reference_does(monkeypatch):
+    """tests/ref_callsite.py (the comparator of the GPU drop-in tests, needed because /root/reference is absent on the GPU
+    box) is run against the same recording rasterizer stub as the reference was: every argument it hands the operator --
+    settings, rescaled means / covariances, relaid SH, fake depth colours of all four modes, background, flags, the
+    zero means2D leaf -- must equal what the reference's render_cuda / render_depth_cuda handed over."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_camera_golden as mk
+    from tests import ref_callsite
+    monkeypatch.setattr(ref_callsite, "GaussianRasterizer", mk._Recorder)
+    monkeypatch.setattr(ref_callsite, "GaussianRasterizationSettings", mk._Settings)
+    z = np.load(GOLDEN)
+    t = lambda k: torch.from_numpy(z[k])
+    ext, intr, near, far, means, cov, sh, opac = (t(k) for k in ("extrinsics", "intrinsics", "near", "far", "means",
+                                                                  "covariances", "sh", "opacities"))
+    B = ext.shape[0]
+
+    def recorded(keys):
+        out = {k: torch.stack([r[k] for r in mk.RECORDED]).numpy() for k in keys}
+        mk.RECORDED.clear()
+        return out
+
+    same = lambda a, b, name: np.testing.assert_allclose(a, b, rtol=2e-6, atol=2e-6, err_msg=name)
+    mk.RECORDED.clear()
+    for tag, si in (("si", True), ("raw", False)):
+        ref_callsite.render_like_reference(ext, intr, near, far, (16, 24), torch.zeros(B, 3), means, cov, sh, opac,
+                                           scale_invariant=si)
+        got = recorded(("viewmatrix", "projmatrix", "campos", "tanfov", "means", "cov6"))
+        for k, v in got.items():
+            same(v, z[f"{tag}_{k}"], f"{tag}_{k}")
+    bg = torch.rand(B, 3, generator=torch.Generator().manual_seed(14))
+    ref_callsite.render_like_reference(ext, intr, near, far, (16, 24), bg, means, cov, sh, opac)
+    for k, v in recorded(("shs", "bg", "opacities", "ints", "scale_modifier", "means2D_is_zero_leaf")).items():
+        same(v, z[f"color_{k}"], f"color_{k}")
+    for mode in ("depth", "disparity", "relative_disparity", "log"):
+        ref_callsite.render_depth_like_reference(ext, intr, near, far, (16, 24), means.abs() + 0.5, cov, opac, mode=mode)
+        for k, v in recorded(("colors", "bg", "opacities", "ints", "scale_modifier", "means2D_is_zero_leaf")).items():
+            same(v, z[f"depth_{mode}_{k}"], f"depth_{mode}_{k}")
