@@ -30,7 +30,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pf3plat_b200.adapter import GaussianAdapter, GaussianAdapterCfg  # noqa: E402
 from pf3plat_b200.metrics import compute_psnr, compute_ssim  # noqa: E402
 from pf3plat_b200.render import decoder_forward  # noqa: E402
-from pf3plat_b200.synthetic import FX, FY, make_cameras  # noqa: E402
+from pf3plat_b200.synthetic import make_cameras  # noqa: E402
 
 H = W = int(os.environ.get("C5_HW", 256))
 SCENES_PER_RANK = int(os.environ.get("C5_SCENES", 1))   # re10k.yaml batch size per GPU
