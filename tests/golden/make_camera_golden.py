@@ -75,6 +75,48 @@ def load_reference_render_cuda():
             del sys.modules["diff_gaussian_rasterization"]
 
 
+def load_reference_decoder():
+    """The reference's DecoderSplattingCUDA (/root/reference/src/model/decoder/decoder_splatting_cuda.py), on top of
+    load_reference_render_cuda(); `src.dataset` (which pulls in every dataset class) is replaced by an empty stand-in --
+    the decoder only reads dataset_cfg.background_color."""
+    load_reference_render_cuda()
+    ds = types.ModuleType("src.dataset")
+    ds.DatasetCfg = type("DatasetCfg", (), {})
+    sys.modules["src.dataset"] = ds
+    for name, rel in (("src.model.types", "src/model/types.py"), ("src.model.decoder.decoder", "src/model/decoder/decoder.py"),
+                      ("src.model.decoder.decoder_splatting_cuda", "src/model/decoder/decoder_splatting_cuda.py")):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REF_ROOT, rel))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+    return sys.modules["src.model.decoder.decoder_splatting_cuda"], sys.modules["src.model.types"]
+
+
+DECODER_KEYS = ("viewmatrix", "projmatrix", "campos", "tanfov", "means", "cov6", "bg", "opacities", "colors", "shs", "ints")
+
+
+def run_reference_decoder(b=2, v=3, G=2, depth_mode="depth"):
+    """Inputs and the recorded operator calls of one DecoderSplattingCUDA.forward (colour pass, then depth pass)."""
+    dec_mod, types_mod = load_reference_decoder()
+    ext, intr, near, far = make_cameras(21, b * v)
+    g = torch.Generator().manual_seed(22)
+    means = torch.randn(b, G, 3, generator=g).abs() + 0.5
+    a = torch.randn(b, G, 3, 3, generator=g)
+    cov = a @ a.transpose(-1, -2)
+    sh = torch.randn(b, G, 3, 25, generator=g)
+    opac = torch.rand(b, G, generator=g)
+    cfg = types.SimpleNamespace(background_color=[0.1, 0.2, 0.3])
+    dec = dec_mod.DecoderSplattingCUDA(dec_mod.DecoderSplattingCUDACfg(name="splatting_cuda"), cfg)
+    RECORDED.clear()
+    r4 = lambda t: t.reshape(b, v, *t.shape[1:])
+    dec.forward(types_mod.Gaussians(means, cov, sh, opac), r4(ext), r4(intr), r4(near), r4(far), (16, 24), depth_mode=depth_mode)
+    rec = {k: [r[k] for r in RECORDED] for k in DECODER_KEYS}
+    RECORDED.clear()
+    inputs = dict(extrinsics=r4(ext), intrinsics=r4(intr), near=r4(near), far=r4(far), means=means, covariances=cov, sh=sh,
+                  opacities=opac)
+    return inputs, rec
+
+
 def make_cameras(seed, B):
     g = torch.Generator().manual_seed(seed)
     ext = torch.eye(4).repeat(B, 1, 1)
@@ -122,6 +164,13 @@ def main():
         arrays[f"color_{k}"] = torch.stack([r[k] for r in RECORDED]).numpy()
     arrays["sh"] = sh.numpy()
     arrays["opacities"] = opac.numpy()
+    # the decoder on top (decoder_splatting_cuda.py:35-91): 2 scenes x 3 views, colour pass then depth pass
+    inputs, rec = run_reference_decoder()
+    for k, t in inputs.items():
+        arrays[f"dec_in_{k}"] = t.numpy()
+    for k, lst in rec.items():
+        for half, sl in (("color", slice(0, 6)), ("depth", slice(6, 12))):
+            arrays[f"dec_{half}_{k}"] = torch.stack(lst[sl]).numpy()
     path = os.path.join(HERE, "camera_glue.npz")
     np.savez_compressed(path, **arrays)
     print({k: v.shape for k, v in arrays.items()}, os.path.getsize(path), "bytes")

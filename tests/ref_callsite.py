@@ -85,3 +85,23 @@ def render_depth_like_reference(extrinsics, intrinsics, near, far, image_shape, 
                                    gaussian_covariances, fake[..., None, None].expand(-1, -1, 3, 1), gaussian_opacities,
                                    scale_invariant=scale_invariant, use_sh=False)
     return result.mean(dim=1)
+
+
+def decoder_like_reference(means, covariances, harmonics, opacities, extrinsics, intrinsics, near, far, image_shape,
+                           background_color, depth_mode=None):
+    """Restates DecoderSplattingCUDA.forward / .render_depth
+    (/root/reference/src/model/decoder/decoder_splatting_cuda.py:35-91): cameras flattened to (b v), the Gaussians of
+    each scene REPEATED v times ("b g ... -> (b v) g ..."), one colour render and -- if depth_mode is given -- a second
+    render for the depth.  Returns (color (b,v,3,h,w), depth (b,v,h,w) or None)."""
+    b, v = extrinsics.shape[:2]
+    flat = lambda t: t.reshape(b * v, *t.shape[2:])
+    rep = lambda t: t.repeat_interleave(v, dim=0)
+    color = render_like_reference(flat(extrinsics), flat(intrinsics), flat(near), flat(far), image_shape,
+                                  background_color[None].expand(b * v, 3), rep(means), rep(covariances), rep(harmonics),
+                                  rep(opacities))
+    color = color.reshape(b, v, *color.shape[1:])
+    if depth_mode is None:
+        return color, None
+    depth = render_depth_like_reference(flat(extrinsics), flat(intrinsics), flat(near), flat(far), image_shape, rep(means),
+                                        rep(covariances), rep(opacities), mode=depth_mode)
+    return color, depth.reshape(b, v, *depth.shape[1:])

@@ -92,3 +92,27 @@ def test_callsite_restatement_hands_the_op_what_the_reference_does(monkeypatch):
         ref_callsite.render_depth_like_reference(ext, intr, near, far, (16, 24), means.abs() + 0.5, cov, opac, mode=mode)
         for k, v in recorded(("colors", "bg", "opacities", "ints", "scale_modifier", "means2D_is_zero_leaf")).items():
             same(v, z[f"depth_{mode}_{k}"], f"depth_{mode}_{k}")
+
+
+def test_decoder_restatement_hands_the_op_what_the_reference_decoder_does(monkeypatch):
+    """ref_callsite.decoder_like_reference against the recorded operator calls of the reference's own
+    DecoderSplattingCUDA.forward (2 scenes x 3 views, colour pass then depth pass): same views in the same order, the
+    same repeated Gaussians, background and fake depth colours."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_camera_golden as mk
+    from tests import ref_callsite
+    monkeypatch.setattr(ref_callsite, "GaussianRasterizer", mk._Recorder)
+    monkeypatch.setattr(ref_callsite, "GaussianRasterizationSettings", mk._Settings)
+    z = np.load(GOLDEN)
+    t = lambda k: torch.from_numpy(z["dec_in_" + k])
+    mk.RECORDED.clear()
+    color, depth = ref_callsite.decoder_like_reference(t("means"), t("covariances"), t("sh"), t("opacities"), t("extrinsics"),
+                                                       t("intrinsics"), t("near"), t("far"), (16, 24),
+                                                       torch.tensor([0.1, 0.2, 0.3]), depth_mode="depth")
+    assert color.shape == (2, 3, 3, 16, 24) and depth.shape == (2, 3, 16, 24) and len(mk.RECORDED) == 12
+    for half, sl in (("color", slice(0, 6)), ("depth", slice(6, 12))):
+        for k in mk.DECODER_KEYS:
+            got = torch.stack([r[k] for r in mk.RECORDED[sl]]).numpy()
+            np.testing.assert_allclose(got, z[f"dec_{half}_{k}"], rtol=2e-6, atol=2e-6, err_msg=f"{half}_{k}")
+    mk.RECORDED.clear()
