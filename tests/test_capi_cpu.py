@@ -146,6 +146,15 @@ def test_reference_render_glue_imports_and_reaches_our_operator_unmodified():
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             mod.render_cuda(sc.extrinsics, sc.intrinsics, sc.near, sc.far, sc.image_shape, sc.background,
                             rep(sc.means), rep(sc.covariances), rep(sc.harmonics), rep(sc.opacities))
+        # the other two call sites of the extension (:192-217 with 0-dim tensor tanfov, :255-268 via render_depth_cuda)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            mod.render_depth_cuda(sc.extrinsics, sc.intrinsics, sc.near, sc.far, sc.image_shape, rep(sc.means),
+                                  rep(sc.covariances), rep(sc.opacities), mode="disparity")
+        one = lambda t: t[:1]
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            mod.render_cuda_orthographic(one(sc.extrinsics), torch.tensor([2.0]), torch.tensor([2.0]), one(sc.near),
+                                         one(sc.far), sc.image_shape, one(sc.background), one(rep(sc.means)),
+                                         one(rep(sc.covariances)), one(rep(sc.harmonics)), one(rep(sc.opacities)))
     finally:
         for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
             del sys.modules[k]
