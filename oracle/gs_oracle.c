@@ -276,6 +276,13 @@ int gso_set_threads(int n) {
 #endif
 }
 
+/* Fragility bookkeeping only: two consecutive contributors of a pixel whose fp32 depths lie within this many ulps are
+ * flagged as an undecided order (default 4).  0 switches the flag off -- for checking an implementation whose depth
+ * keys are bit-identical to this file's (same fma chain), in regimes where exact ties are the rule (the
+ * fake-orthographic camera of cuda_splatting.py:154-165 puts every depth near 1.2e3, where fp32 resolves 1.2e-4). */
+static float g_depth_tie_ulps = 4.0f;
+void gso_set_depth_tie_ulps(float u) { g_depth_tie_ulps = u; }
+
 int gso_real_size(void) { return (int)sizeof(real); }
 int gso_params_size(void) { return (int)sizeof(gso_params); }
 
@@ -521,7 +528,7 @@ gso_handle *gso_forward(const gso_params *pp, const real *means3D, const real *s
                     if (test_T < RL(0.0001)) break; /* done; this Gaussian is NOT added */
                     if (frag_rel > 0) {
                         float dcur = (float)h->depths[id];
-                        if (last_depth > 0 && fabsf(dcur - last_depth) <= 4.0f * 1.1920929e-7f * dcur) frag = 1;
+                        if (last_depth > 0 && g_depth_tie_ulps > 0 && fabsf(dcur - last_depth) <= g_depth_tie_ulps * 1.1920929e-7f * dcur) frag = 1;
                         last_depth = dcur;
                     }
                     const real *col = h->rgb + 3 * (size_t)id;

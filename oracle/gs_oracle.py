@@ -33,6 +33,12 @@ def set_threads(n: int) -> int:
     return min(int(_lib(d).gso_set_threads(int(n))) for d in (np.float32, np.float64))
 
 
+def set_depth_tie_ulps(ulps: float) -> None:
+    """Fragility flags only: width (in fp32 ulps) of the "undecided depth order" band; 0 disables it (see gs_oracle.c)."""
+    for d in (np.float32, np.float64):
+        _lib(d).gso_set_depth_tie_ulps(ctypes.c_float(ulps))
+
+
 def _lib(dtype) -> ctypes.CDLL:
     name = "f64" if np.dtype(dtype) == np.float64 else "f32"
     if name not in _LIBS:
@@ -47,6 +53,8 @@ def _lib(dtype) -> ctypes.CDLL:
         lib.gso_free.argtypes = [ctypes.c_void_p]
         lib.gso_set_threads.restype = ctypes.c_int
         lib.gso_set_threads.argtypes = [ctypes.c_int]
+        lib.gso_set_depth_tie_ulps.restype = None
+        lib.gso_set_depth_tie_ulps.argtypes = [ctypes.c_float]
         for f in ("gso_num_rendered", "gso_num_visible", "gso_num_pairs"):
             getattr(lib, f).restype = ctypes.c_int64
             getattr(lib, f).argtypes = [ctypes.c_void_p]

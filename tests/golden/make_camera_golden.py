@@ -117,6 +117,12 @@ def run_reference_decoder(b=2, v=3, G=2, depth_mode="depth"):
     return inputs, rec
 
 
+def ortho_inputs():
+    ext = make_cameras(31, 1)[0]
+    return dict(extrinsics=ext, width=torch.tensor([2.5]), height=torch.tensor([1.75]), near=torch.tensor([0.0]),
+                far=torch.tensor([7.0]), bg=torch.tensor([[0.3, 0.1, 0.2]]))
+
+
 def make_cameras(seed, B):
     g = torch.Generator().manual_seed(seed)
     ext = torch.eye(4).repeat(B, 1, 1)
@@ -164,6 +170,18 @@ def main():
         arrays[f"color_{k}"] = torch.stack([r[k] for r in RECORDED]).numpy()
     arrays["sh"] = sh.numpy()
     arrays["opacities"] = opac.numpy()
+    # the fake-orthographic render (render_cuda_orthographic, :130-220; batch of one, as its 0-dim/1-element tensor
+    # tanfov arguments require): everything it hands the op
+    for k, t in ortho_inputs().items():
+        arrays[f"ortho_in_{k}"] = t.numpy()
+    RECORDED.clear()
+    oi = ortho_inputs()
+    mod.render_cuda_orthographic(oi["extrinsics"], oi["width"], oi["height"], oi["near"], oi["far"], (16, 24), oi["bg"],
+                                 means[:1], cov[:1], sh[:1], opac[:1])
+    assert len(RECORDED) == 1
+    for k in ("viewmatrix", "projmatrix", "campos", "tanfov", "means", "cov6", "shs", "bg", "opacities", "ints",
+              "scale_modifier", "means2D_is_zero_leaf"):
+        arrays[f"ortho_{k}"] = torch.stack([r[k] for r in RECORDED]).numpy()
     # the decoder on top (decoder_splatting_cuda.py:35-91): 2 scenes x 3 views, colour pass then depth pass
     inputs, rec = run_reference_decoder()
     for k, t in inputs.items():

@@ -105,3 +105,73 @@ def decoder_like_reference(means, covariances, harmonics, opacities, extrinsics,
     depth = render_depth_like_reference(flat(extrinsics), flat(intrinsics), flat(near), flat(far), image_shape, rep(means),
                                         rep(covariances), rep(opacities), mode=depth_mode)
     return color, depth.reshape(b, v, *depth.shape[1:])
+
+
+def orthographic_settings_like_reference(extrinsics, width, height, near, far, image_shape, background_color, d_sh,
+                                         fov_degrees: float = 0.1):
+    """The camera part of render_cuda_orthographic (/root/reference/src/model/decoder/cuda_splatting.py:154-177, :192-205):
+    a fake "orthographic" projection -- tiny field of view, camera moved back along its own z axis.  Returns one dict per
+    view with the fields the reference puts into GaussianRasterizationSettings (numpy, for the oracle) plus the tensors."""
+    b = extrinsics.shape[0]
+    h, w = image_shape
+    fov_x = torch.tensor(fov_degrees, device=extrinsics.device).deg2rad()
+    tan_fov_x = (0.5 * fov_x).tan()
+    distance_to_near = (0.5 * width) / tan_fov_x
+    tan_fov_y = 0.5 * height / distance_to_near
+    fov_y = (2 * tan_fov_y).atan()
+    near = near + distance_to_near
+    far = far + distance_to_near
+    move_back = torch.eye(4, dtype=torch.float32, device=extrinsics.device)
+    move_back[2, 3] = -distance_to_near
+    extrinsics = extrinsics @ move_back
+    projection_matrix = get_projection_matrix(near, far, fov_x.expand(b), fov_y).transpose(-1, -2)
+    view_matrix = extrinsics.inverse().transpose(-1, -2)
+    full_projection = view_matrix @ projection_matrix
+    out = []
+    for i in range(b):
+        out.append(dict(tanfovx=tan_fov_x, tanfovy=tan_fov_y[i] if tan_fov_y.dim() else tan_fov_y, bg=background_color[i],
+                        viewmatrix_t=view_matrix[i], projmatrix_t=full_projection[i], campos_t=extrinsics[i, :3, 3],
+                        sh_degree=isqrt(d_sh) - 1))
+    for d in out:
+        d["viewmatrix"] = d["viewmatrix_t"].detach().cpu().numpy()
+        d["projmatrix"] = d["projmatrix_t"].detach().cpu().numpy()
+        d["campos"] = d["campos_t"].detach().cpu().numpy()
+        d["tanfovx"], d["tanfovy"] = float(d["tanfovx"]), float(d["tanfovy"])
+    return out
+
+
+def render_orthographic_like_reference(extrinsics, width, height, near, far, image_shape, background_color,
+                                       gaussian_means, gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities,
+                                       fov_degrees: float = 0.1, use_sh: bool = True):
+    """Restates render_cuda_orthographic (cuda_splatting.py:130-220).  Unlike render_cuda it passes the 0-dim TENSOR
+    tan_fov_x / tan_fov_y into the settings (:195-196), not `.item()` floats."""
+    b = extrinsics.shape[0]
+    h, w = image_shape
+    assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
+    n = gaussian_sh_coefficients.shape[-1]
+    shs = gaussian_sh_coefficients.permute(0, 1, 3, 2).contiguous()
+    sts = orthographic_settings_like_reference(extrinsics, width, height, near, far, image_shape, background_color, n,
+                                               fov_degrees)
+    fov_x = torch.tensor(fov_degrees, device=extrinsics.device).deg2rad()
+    tan_fov_x = (0.5 * fov_x).tan()
+    distance_to_near = (0.5 * width) / tan_fov_x
+    tan_fov_y = 0.5 * height / distance_to_near
+    all_images = []
+    for i in range(b):
+        mean_gradients = torch.zeros_like(gaussian_means[i], requires_grad=True)
+        try:
+            mean_gradients.retain_grad()
+        except Exception:
+            pass
+        settings = GaussianRasterizationSettings(
+            image_height=h, image_width=w, tanfovx=tan_fov_x, tanfovy=tan_fov_y, bg=background_color[i],
+            scale_modifier=1.0, viewmatrix=sts[i]["viewmatrix_t"], projmatrix=sts[i]["projmatrix_t"],
+            sh_degree=sts[i]["sh_degree"], campos=sts[i]["campos_t"], prefiltered=False, debug=False)
+        rasterizer = GaussianRasterizer(settings)
+        row, col = torch.triu_indices(3, 3)
+        image, radii = rasterizer(
+            means3D=gaussian_means[i], means2D=mean_gradients, shs=shs[i] if use_sh else None,
+            colors_precomp=None if use_sh else shs[i, :, 0, :], opacities=gaussian_opacities[i, ..., None],
+            cov3D_precomp=gaussian_covariances[i, :, row, col])
+        all_images.append(image)
+    return torch.stack(all_images)

@@ -94,6 +94,39 @@ def test_callsite_restatement_hands_the_op_what_the_reference_does(monkeypatch):
             same(v, z[f"depth_{mode}_{k}"], f"depth_{mode}_{k}")
 
 
+def test_orthographic_restatement_hands_the_op_what_the_reference_does(monkeypatch):
+    """ref_callsite.render_orthographic_like_reference against the recorded operator call of the reference's own
+    render_cuda_orthographic (cuda_splatting.py:130-220): the moved-back camera, the 0.1-degree field of view, the
+    projection built from it."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_camera_golden as mk
+    from tests import ref_callsite
+    monkeypatch.setattr(ref_callsite, "GaussianRasterizer", mk._Recorder)
+    monkeypatch.setattr(ref_callsite, "GaussianRasterizationSettings", mk._Settings)
+    z = np.load(GOLDEN)
+    t = lambda k: torch.from_numpy(z[k])
+    oi = {k: t("ortho_in_" + k) for k in ("extrinsics", "width", "height", "near", "far", "bg")}
+    mk.RECORDED.clear()
+    ref_callsite.render_orthographic_like_reference(oi["extrinsics"], oi["width"], oi["height"], oi["near"], oi["far"],
+                                                    (16, 24), oi["bg"], t("means")[:1], t("covariances")[:1], t("sh")[:1],
+                                                    t("opacities")[:1])
+    assert len(mk.RECORDED) == 1
+    for k in ("viewmatrix", "projmatrix", "campos", "tanfov", "means", "cov6", "shs", "bg", "opacities", "ints",
+              "scale_modifier", "means2D_is_zero_leaf"):
+        got = torch.stack([r[k] for r in mk.RECORDED]).numpy()
+        want = z[f"ortho_{k}"]
+        np.testing.assert_allclose(got, want, rtol=2e-6, atol=2e-6 * max(1.0, float(np.abs(want).max())), err_msg=k)
+    assert abs(z["ortho_viewmatrix"][0, 3, 2]) > 1000 and z["ortho_tanfov"][0, 0] < 1e-3   # the stressed regime
+    mk.RECORDED.clear()
+    # the settings helper the GPU test feeds the oracle with is the same computation
+    st = ref_callsite.orthographic_settings_like_reference(oi["extrinsics"], oi["width"], oi["height"], oi["near"],
+                                                           oi["far"], (16, 24), oi["bg"], 25)[0]
+    np.testing.assert_allclose(st["viewmatrix"], z["ortho_viewmatrix"][0], rtol=2e-6, atol=2e-3)
+    np.testing.assert_allclose(st["projmatrix"], z["ortho_projmatrix"][0], rtol=2e-6, atol=2e-3)
+    np.testing.assert_allclose([st["tanfovx"], st["tanfovy"]], z["ortho_tanfov"][0], rtol=1e-6)
+
+
 def test_decoder_restatement_hands_the_op_what_the_reference_decoder_does(monkeypatch):
     """ref_callsite.decoder_like_reference against the recorded operator calls of the reference's own
     DecoderSplattingCUDA.forward (2 scenes x 3 views, colour pass then depth pass): same views in the same order, the

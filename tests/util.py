@@ -52,3 +52,100 @@ def simple_settings(h=64, w=64, tanfov=0.5, bg=(0.0, 0.0, 0.0), near=1.0, far=10
     return OracleSettings(image_height=h, image_width=w, tanfovx=tanfov, tanfovy=tanfov, bg=np.array(bg, np.float64),
                           scale_modifier=1.0, viewmatrix=view.T.copy(), projmatrix=full, sh_degree=sh_degree,
                           campos=np.zeros(3))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# parity criteria (BASELINE.json north_star: 1e-4 abs RGB, 1e-3 rel gradient)
+# ---------------------------------------------------------------------------------------------------------
+RGB_TOL = 1e-4          # non-fragile pixels
+FRAGILE_RGB_TOL = 5e-3  # pixels where the oracle saw a discontinuous decision within 1e-4 of its threshold: ONE flipped
+                        # alpha >= 1/255 decision moves a channel by at most alpha*T*c <= 1/255 = 3.9e-3
+GRAD_RTOL = 1e-3        # element-wise: |a-b| <= GRAD_RTOL*|b| + GRAD_RTOL*rms(b), per tensor and per SH band
+GRAD_RTOL_AFFECTED = 2e-2  # same form, for Gaussians that contribute to a fragile pixel (their T chain may differ by one
+                           # flipped 1/255-alpha decision, a <= 0.4 % effect)
+
+
+def image_report(gpu_color, orc) -> dict:
+    """The four numbers SURVEY.md section 7 asks for, of one view against the oracle."""
+    g = gpu_color.detach().cpu().numpy() if torch.is_tensor(gpu_color) else np.asarray(gpu_color)
+    err = np.abs(g.astype(np.float64) - orc.color.astype(np.float64)).max(axis=0)
+    frag = orc.px_fragile
+    return {
+        "pixels": int(err.size),
+        "pixels_over_1e-4": int((err > RGB_TOL).sum()),
+        "nonfragile_pixels_over_1e-4": int((err[~frag] > RGB_TOL).sum()),
+        "fragile_frac": float(frag.mean()),
+        "max_err_nonfragile": float(err[~frag].max()) if (~frag).any() else 0.0,
+        "max_err_fragile": float(err[frag].max()) if frag.any() else 0.0,
+    }
+
+
+def check_image_strict(gpu_color, orc, max_fragile_frac: float, label: str = "") -> dict:
+    rep = image_report(gpu_color, orc)
+    print(f"[parity] {label} {rep}")
+    assert rep["fragile_frac"] <= max_fragile_frac, rep
+    assert rep["max_err_nonfragile"] <= RGB_TOL, rep
+    assert rep["max_err_fragile"] <= FRAGILE_RGB_TOL, rep
+    return rep
+
+
+def affected_gaussians(orc, pixel_mask: np.ndarray) -> np.ndarray:
+    """bool[P]: Gaussians that can contribute (alpha >= ~1/255) to a pixel of `pixel_mask` -- a flipped decision at such a
+    pixel changes T for every Gaussian behind it there, so their gradients carry the fragile pixel's slack."""
+    P = orc.P
+    hit = np.zeros(P, bool)
+    ys, xs = np.nonzero(pixel_mask)
+    if len(ys) == 0:
+        return hit
+    xy, co, pl, rg = orc.xy.astype(np.float64), orc.conic_opacity.astype(np.float64), orc.point_list, orc.ranges
+    gx = (orc.W + 15) // 16
+    tiles = (ys // 16) * gx + (xs // 16)
+    for t in np.unique(tiles):
+        s, e = rg[t]
+        ids = pl[s:e]
+        if len(ids) == 0:
+            continue
+        sel = tiles == t
+        px, py = xs[sel][None, :].astype(np.float64), ys[sel][None, :].astype(np.float64)
+        dx, dy = xy[ids, 0:1] - px, xy[ids, 1:2] - py
+        power = -0.5 * (co[ids, 0:1] * dx * dx + co[ids, 2:3] * dy * dy) - co[ids, 1:2] * dx * dy
+        alpha = co[ids, 3:4] * np.exp(np.minimum(power, 0.0))
+        touch = ((power <= 1e-6) & (alpha >= (1 / 255) * 0.99)).any(axis=1)
+        hit[ids[touch]] = True
+    return hit
+
+
+def grad_report(name, a, b, affected=None, bands=None) -> dict:
+    """Element-wise gradient criterion.  a: ours, b: oracle, both [P, ...]; affected: bool[P] or None; bands: list of
+    (label, slice over axis 1) to apply the criterion per SH band (rms taken per band)."""
+    a = a.detach().cpu().numpy().astype(np.float64) if torch.is_tensor(a) else np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64).reshape(a.shape)
+    P = a.shape[0]
+    aff = np.zeros(P, bool) if affected is None else affected
+    out = {"name": name, "elements": int(a.size), "affected_gaussians": int(aff.sum())}
+    worst_ok, worst_aff, bad, bad_aff = 0.0, 0.0, 0, 0
+    parts = [("all", slice(None))] if bands is None else bands
+    for label, sl in parts:
+        aa, bb = (a, b) if bands is None else (a[:, sl], b[:, sl])
+        rms = float(np.sqrt(np.mean(bb * bb)))
+        ratio = np.abs(aa - bb) / (np.abs(bb) + rms + 1e-300)   # criterion: ratio <= rtol
+        r2 = ratio.reshape(P, -1).max(axis=1) if ratio.size else np.zeros(P)
+        worst_ok = max(worst_ok, float(r2[~aff].max()) if (~aff).any() else 0.0)
+        worst_aff = max(worst_aff, float(r2[aff].max()) if aff.any() else 0.0)
+        bad += int((r2[~aff] > GRAD_RTOL).sum())
+        bad_aff += int((r2[aff] > GRAD_RTOL_AFFECTED).sum())
+        out[f"rms_{label}"] = rms
+    out.update(worst_ratio_unaffected=worst_ok, worst_ratio_affected=worst_aff, gaussians_over_tol=bad,
+               affected_over_loose_tol=bad_aff)
+    return out
+
+
+SH_BANDS = [("band0", slice(0, 1)), ("band1", slice(1, 4)), ("band2", slice(4, 9)), ("band3", slice(9, 16))]
+
+
+def check_grad(name, a, b, affected=None, bands=None) -> dict:
+    rep = grad_report(name, a, b, affected, bands)
+    print(f"[parity] grad {rep}")
+    assert rep["gaussians_over_tol"] == 0, rep
+    assert rep["affected_over_loose_tol"] == 0, rep
+    return rep
