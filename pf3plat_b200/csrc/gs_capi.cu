@@ -590,7 +590,7 @@ extern "C" int gs_backward(GsContext *ctx, const GsConfig *cfg, const GsInputs *
     {
         StageTimer t(ctx, GS_STAGE_COMPOSITE_BWD, st);
         GS_CUDA_OK(cudaMemsetAsync(acc, 0, n * GS_ACC_STRIDE * 4, st));
-        rc = launch_composite_bwd(c, *saved, gout->dL_dcolor, gout->dL_ddepth, acc, st);
+        rc = launch_composite_bwd(c, *saved, gout->dL_dcolor, gout->dL_ddepth, acc, st, (cfg->tuning & GS_TUNE_BWD_V1) ? 1 : 0);
         if (rc != GS_OK) return rc;
     }
     {

@@ -1,20 +1,19 @@
 """GPU parity tests: the sm_100a kernels, called through the C ABI, against the CPU oracle on the same seeded
-inputs.  Tolerances are BASELINE.json's: 1e-4 abs RGB, 1e-3 rel gradient (relative to each tensor's max-abs).
+inputs.  Tolerances are BASELINE.json's: 1e-4 abs RGB, 1e-3 rel gradient -- the gradient criterion is ELEMENT-WISE,
+|a-b| <= 1e-3 |b| + 1e-3 rms(b), per tensor and per SH band (tests/util.py).
 Pixels the oracle flags as FRAGILE (a discontinuous decision -- alpha<1/255, T<1e-4, ceil/int of the footprint,
 near-equal depths -- lies within 1e-4 relative of its threshold, so two correct fp32 implementations may take
-either branch) are held to a looser 1/255-class bound and must be a small fraction of the image."""
+either branch) are held to 5e-3 (one flipped 1/255-alpha decision is worth <= 3.9e-3) and must be a small fraction of
+the image; Gaussians that contribute to such a pixel carry a 2e-2 gradient bound.  Every check prints its numbers."""
 import numpy as np
 import pytest
 import torch
 
 from pf3plat_b200.synthetic import make_scene, make_target
-from tests.util import oracle_view, view_args
+from tests.util import (FRAGILE_RGB_TOL, RGB_TOL, SH_BANDS, affected_gaussians, check_grad, image_report, oracle_view,
+                        view_args)
 
 pytestmark = pytest.mark.gpu
-
-RGB_TOL = 1e-4
-GRAD_TOL = 1e-3
-FRAGILE_RGB_TOL = 2e-2
 
 
 def _dev():
@@ -22,15 +21,17 @@ def _dev():
     return torch.device("cuda:0")
 
 
-def check_image(gpu_color, orc, max_fragile_frac=0.05):
-    err = np.abs(gpu_color.detach().cpu().numpy().astype(np.float64) - orc.color.astype(np.float64)).max(axis=0)
-    frag = orc.px_fragile
-    assert frag.mean() <= max_fragile_frac, f"fragile fraction {frag.mean()}"
-    if (~frag).any():
-        assert err[~frag].max() <= RGB_TOL, f"max abs RGB error {err[~frag].max()} on non-fragile pixels"
-    if frag.any():
-        assert err[frag].max() <= FRAGILE_RGB_TOL, f"fragile pixel error {err[frag].max()}"
-    return err
+def check_image(gpu_color, orc, max_fragile_frac=0.03):
+    rep = image_report(gpu_color, orc)
+    print(f"[parity] {rep}")
+    assert rep["fragile_frac"] <= max_fragile_frac, rep
+    assert rep["max_err_nonfragile"] <= RGB_TOL, rep
+    assert rep["max_err_fragile"] <= FRAGILE_RGB_TOL, rep
+    return rep
+
+
+def affected_of(orc):
+    return affected_gaussians(orc, orc.px_fragile) | orc.geom_fragile
 
 
 def check_radii(gpu_radii, orc):
@@ -125,10 +126,10 @@ def test_backward_matches_oracle(mode):
     check_image(color, orc)
     check_radii(radii, orc)
     (color * torch.tensor(dL, device=dev)).sum().backward()
+    aff = affected_of(orc)
     for name, t in tk.items():
-        e = relerr(t.grad, g_ref[name])
-        assert e <= GRAD_TOL, (name, e)
-    assert relerr(m2d.grad, g_ref["means2D"]) <= GRAD_TOL
+        check_grad(f"{mode} dL/d{name}", t.grad, g_ref[name], aff, bands=SH_BANDS if name == "shs" else None)
+    check_grad(f"{mode} dL/dmeans2D", m2d.grad, g_ref["means2D"], aff)
 
 
 def test_batched_backward_sums_views_and_matches_oracle():
@@ -141,8 +142,10 @@ def test_batched_backward_sums_views_and_matches_oracle():
     loss = ((color - target) ** 2).mean() + wd * depth.mean()
     loss.backward()
     gm = np.zeros((6000, 3)); go = np.zeros(6000); gs = np.zeros((6000, 25, 3)); gc = np.zeros((6000, 6))
+    aff = np.zeros(6000, bool)
     for v in range(views):
         orc = oracle_view(sc, v, with_depth=True)
+        aff |= affected_of(orc)
         check_image(color[v], orc)
         derr = np.abs(depth[v].detach().cpu().numpy() - orc.depth)[~orc.px_fragile].max()
         assert derr <= 1e-3, derr      # depth values reach ~20: 1e-3 abs is ~5e-5 relative
@@ -150,13 +153,13 @@ def test_batched_backward_sums_views_and_matches_oracle():
         dLd = np.full((64, 64), wd / (views * 64 * 64), np.float32)
         g = orc.backward(dL, dLd)
         gm += g["means3D"]; go += g["opacities"][:, 0]; gs += g["shs"]; gc += g["cov3D_precomp"]
-    assert relerr(leaves["means"].grad[0], gm) <= GRAD_TOL
-    assert relerr(leaves["opac"].grad[0], go) <= GRAD_TOL
-    assert relerr(leaves["sh"].grad[0].permute(0, 2, 1), gs) <= GRAD_TOL
+    check_grad("batched dL/dmeans", leaves["means"].grad[0], gm, aff)
+    check_grad("batched dL/dopacities", leaves["opac"].grad[0].reshape(-1, 1), go.reshape(-1, 1), aff)
+    check_grad("batched dL/dshs", leaves["sh"].grad[0].permute(0, 2, 1), gs, aff, bands=SH_BANDS)
     # covariance gradient arrives on the (3,3) matrix; fold it to the 6 unique entries
     G = leaves["cov"].grad[0].cpu().numpy()
     g6 = np.stack([G[:, 0, 0], G[:, 0, 1], G[:, 0, 2], G[:, 1, 1], G[:, 1, 2], G[:, 2, 2]], -1)
-    assert relerr(g6, gc) <= GRAD_TOL
+    check_grad("batched dL/dcov3D", g6, gc, aff)
 
 
 def test_edge_cases():
@@ -196,7 +199,7 @@ def test_determinism_and_linearity_at_full_size():
     c2, _ = render_batch(sc, dev)
     assert torch.equal(c1, c2)
     orc = oracle_view(sc, 1)
-    check_image(c1[1], orc, max_fragile_frac=0.05)
+    check_image(c1[1], orc)
     g = torch.randn_like(c1)
     (ga,) = torch.autograd.grad((c1 * g).sum(), leaves["means"], retain_graph=True)
     (gb,) = torch.autograd.grad((c1 * (2 * g)).sum(), leaves["means"])
@@ -280,12 +283,14 @@ def test_pixel_aligned_pf3plat_shaped_cloud():
     target = make_target(3, 128, 128).to(dev)
     ((color - target) ** 2).mean().backward()
     gm = 0
+    aff = np.zeros(sc.means.shape[0], bool)
     for v in range(3):
         orc = oracle_view(sc, v)
         check_image(color[v], orc)
+        aff |= affected_of(orc)
         dL = (2 * (orc.color - target[v].cpu().numpy()) / target.numel()).astype(np.float32)
         gm = gm + orc.backward(dL)["means3D"]
-    assert relerr(leaves["means"].grad[0], gm) <= GRAD_TOL
+    check_grad("pixel-aligned dL/dmeans", leaves["means"].grad[0], gm, aff)
     # Depth strata on a cloud whose tiles each see a narrow depth range (a smooth surface): the per-view octiles do
     # not balance such tiles.  Whatever the library decides (strata kept, or dropped for this shape after the trial),
     # every call gives the same pixels.
