@@ -152,6 +152,10 @@ GS_API const char *gs_last_error(void);
 /* Workspace lifetime (upstream allocates scratch through torch callbacks on every call; here it is a grow-only cache). */
 GS_API int gs_context_create(GsContext **out);
 GS_API void gs_context_destroy(GsContext *ctx);
+/* Saved state and scratch come from a PRIVATE stream-ordered memory pool of the context (not the device's default
+ * pool, and outside the caller's allocator).  It keeps about one forward's worth of freed blocks cached; this hands
+ * everything that is not in use back to the driver (call it where the host framework empties its own caches). */
+GS_API int gs_context_trim(GsContext *ctx);
 
 /*
  * Forward = _RasterizeGaussians.forward -> _C.rasterize_gaussians: preprocess,

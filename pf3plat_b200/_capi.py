@@ -20,6 +20,7 @@ GS_TUNE_FORCE_RADIX_BINNING = 1
 GS_TUNE_NO_SPECULATION = 2
 GS_TUNE_SEPARATE_EMIT = 4
 GS_TUNE_NO_STRATA = 8
+GS_TUNE_BWD_V1 = 16
 GS_TUNE_FEED_PIECES_SHIFT = 8
 GS_NUM_STAGES = 7
 STAGE_NAMES = ("preprocess", "bin_scan", "bin_emit", "bin_sort", "composite", "composite_bwd", "preprocess_bwd")
@@ -94,6 +95,7 @@ SYMBOLS = {
     "gs_last_error": (c_char_p, []),
     "gs_context_create": (c_int, [POINTER(c_void_p)]),
     "gs_context_destroy": (None, [c_void_p]),
+    "gs_context_trim": (c_int, [c_void_p]),
     "gs_forward": (c_int, [c_void_p, POINTER(GsConfig), POINTER(GsInputs), POINTER(GsOutputs), POINTER(c_void_p), c_void_p]),
     "gs_backward": (c_int, [c_void_p, POINTER(GsConfig), POINTER(GsInputs), c_void_p, POINTER(GsOutGrads),
                             POINTER(GsInGrads), c_void_p]),

@@ -26,20 +26,29 @@ extern "C" int gs_abi_version(void) { return GS_ABI_VERSION; }
 // ---------------------------------------------------------------------------------------------------------
 // context: grow-only scratch, pinned read-back word, optional stage timers
 // ---------------------------------------------------------------------------------------------------------
+// Grow-only scratch.  With a pool and a stream, growth is stream-ordered (cudaFreeAsync + cudaMallocFromPoolAsync on the
+// context's own stream and pool): no device-wide synchronisation when a bigger batch arrives mid-training.  Without
+// (pool == nullptr: the host-staging buffer, which a second stream writes into) it is cudaFree + cudaMalloc.
 struct GrowBuf {
     void *p = nullptr;
     size_t bytes = 0;
-    int reserve(size_t need, double headroom) {
+    bool pooled = false;
+    int reserve(size_t need, double headroom, cudaMemPool_t pool = nullptr, cudaStream_t st = nullptr) {
         if (need <= bytes) return GS_OK;
-        if (p) GS_CUDA_OK(cudaFree(p));  // implicit device sync: nothing in flight can still use it
+        if (p) {
+            if (pooled) GS_CUDA_OK(cudaFreeAsync(p, st));  // everything that used it was enqueued on st before this point
+            else GS_CUDA_OK(cudaFree(p));                  // implicit device sync
+        }
         p = nullptr;
         bytes = 0;
         size_t want = (size_t)((double)need * headroom) + 256;
-        GS_CUDA_OK(cudaMalloc(&p, want));
+        if (pool) GS_CUDA_OK(cudaMallocFromPoolAsync(&p, want, pool, st));
+        else GS_CUDA_OK(cudaMalloc(&p, want));
+        pooled = pool != nullptr;
         bytes = want;
         return GS_OK;
     }
-    void release() {
+    void release() {  // after a device synchronisation
         if (p) cudaFree(p);
         p = nullptr;
         bytes = 0;
@@ -49,6 +58,12 @@ struct GrowBuf {
 enum { STRATA_UNKNOWN = 0, STRATA_TRIAL = 1, STRATA_ON = 2, STRATA_OFF = 3 };
 
 struct GsContext {
+    // Private stream-ordered pool: saved state (records, lists, image planes) and scratch.  Blocks freed by
+    // gs_saved_free stay cached up to a release threshold that follows the size of ONE forward's saved state (so the
+    // next forward reuses them without touching the OS), never the device's default pool and never unbounded --
+    // gs_context_trim() / gs_context_destroy() hand everything back.
+    cudaMemPool_t pool = nullptr;
+    uint64_t pool_threshold = 0;
     GrowBuf per_gaussian;  // rects | tile counts / offsets / cursors ; backward: accumulators
     GrowBuf sort;          // buckets (fast path) or radix-sort buffers (fallback)
     GrowBuf host_stage;    // device mirror of host buffers (gs_render_host)
@@ -199,17 +214,20 @@ extern "C" int gs_context_create(GsContext **out) {
     if (cudaGetDevice(&dev) != cudaSuccess) return gs_set_error(GS_ERR_NO_DEVICE, "no CUDA device");
     GsContext *ctx = new (std::nothrow) GsContext();
     if (!ctx) return gs_set_error(GS_ERR_OOM, "host allocation failed");
-    // Saved state lives in the device's default stream-ordered pool.  Its default release threshold (0) hands
-    // every freed block back to the OS at the next synchronisation -- and each forward synchronises once -- so
-    // keep freed blocks cached in the pool instead.
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t keep = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaError_t e = cudaMemPoolCreate(&ctx->pool, &props);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return gs_set_cuda_error(e, "cudaMemPoolCreate", __FILE__, __LINE__);
     }
-    cudaError_t e = cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_word), 64, cudaHostAllocMapped);
+    e = cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_word), 64, cudaHostAllocMapped);
     if (e == cudaSuccess) e = cudaHostGetDevicePointer(reinterpret_cast<void **>(&ctx->d_word), ctx->h_word, 0);
     if (e != cudaSuccess) {
+        cudaMemPoolDestroy(ctx->pool);
         delete ctx;
         return gs_set_cuda_error(e, "cudaHostAlloc", __FILE__, __LINE__);
     }
@@ -230,6 +248,7 @@ extern "C" void gs_context_destroy(GsContext *ctx) {
     if (ctx->ev_pre) cudaEventDestroy(ctx->ev_pre);
     if (ctx->ev_info) cudaEventDestroy(ctx->ev_info);
     if (ctx->h_word) cudaFreeHost(ctx->h_word);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);  // outstanding GsSaved blocks are returned when they are freed
     if (ctx->profiling)
         for (auto &e : ctx->ev) {
             if (e[0]) cudaEventDestroy(e[0]);
@@ -237,6 +256,23 @@ extern "C" void gs_context_destroy(GsContext *ctx) {
         }
     delete ctx;
 }
+
+extern "C" int gs_context_trim(GsContext *ctx) {
+    if (!ctx) return gs_set_error(GS_ERR_INVALID, "null context");
+    GS_CUDA_OK(cudaMemPoolTrimTo(ctx->pool, 0));
+    return GS_OK;
+}
+
+namespace {
+// Keep about one forward's worth of freed saved state cached in the pool (the next forward takes it back), no more.
+void pool_follow(GsContext *ctx, size_t saved_bytes) {
+    const uint64_t want = (uint64_t)saved_bytes + (saved_bytes >> 2) + ((uint64_t)16 << 20);
+    if (want > ctx->pool_threshold || want < ctx->pool_threshold / 2) {
+        ctx->pool_threshold = want;
+        cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &ctx->pool_threshold);
+    }
+}
+}  // namespace
 
 extern "C" int gs_set_profiling(GsContext *ctx, int enabled) {
     if (!ctx) return gs_set_error(GS_ERR_INVALID, "null context");
@@ -296,7 +332,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     const size_t nvt = (size_t)c.V * c.ntiles;
     const size_t ctr_bytes = align256(bin_counter_bytes(c));
     const size_t pg_bytes = align256(n * 8) + 2 * ctr_bytes + 256 + align256(nvt * BIN_SUB * 4) + 2 * align256(nvt * 4);
-    rc = ctx->per_gaussian.reserve(pg_bytes, 1.0);
+    rc = ctx->per_gaussian.reserve(pg_bytes, 1.0, ctx->pool, st);
     if (rc != GS_OK) return rc;
     unsigned char *pg = static_cast<unsigned char *>(ctx->per_gaussian.p);
     ushort4 *rects = reinterpret_cast<ushort4 *>(pg);
@@ -320,7 +356,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     {
         const size_t bytes = saved_layout(s, c, nullptr);
         unsigned char *block = nullptr;
-        cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&block), bytes, st);
+        cudaError_t e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&block), bytes, ctx->pool, st);
         if (e != cudaSuccess) {
             delete s;
             return gs_set_cuda_error(e, "cudaMallocAsync(saved)", __FILE__, __LINE__);
@@ -349,9 +385,9 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
         if (strata && sub_cap > BIN_STRATUM_CAP) sub_cap = BIN_STRATUM_CAP;
         const float *strata_tab = strata ? static_cast<const float *>(ctx->strata.p) : nullptr;
         const size_t slots = nvt * BIN_SUB;
-        rc = ctx->sort.reserve(slots * sub_cap * 8, 1.0);
+        rc = ctx->sort.reserve(slots * sub_cap * 8, 1.0, ctx->pool, st);
         if (rc != GS_OK) return fail(rc);
-        cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&s->point_list), slots * sub_cap * 4, st);
+        cudaError_t e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&s->point_list), slots * sub_cap * 4, ctx->pool, st);
         if (e != cudaSuccess) {
             s->point_list = nullptr;
             return fail(gs_set_cuda_error(e, "cudaMallocAsync(point_list)", __FILE__, __LINE__));
@@ -461,6 +497,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
             ctx->stats.num_rendered = D;
             ctx->stats.num_visible = -1;
             ctx->stats.saved_bytes = (int64_t)(s->bytes + slots * sub_cap * 4);
+            pool_follow(ctx, (size_t)ctx->stats.saved_bytes);
             ctx->stats.speculative = strata ? 2 : 1;
             if (saved_out) *saved_out = s;
             else gs_saved_free(ctx, s, stream);
@@ -509,7 +546,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
         }
         if (D > 0x7fffffffll) return fail(gs_set_error(GS_ERR_OVERFLOW, "more than 2^31-1 tile instances"));
         // the list lives in its own stream-ordered allocation (sized exactly)
-        e = cudaMallocAsync(reinterpret_cast<void **>(&s->point_list), (size_t)(D > 0 ? D : 1) * 4, st);
+        e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&s->point_list), (size_t)(D > 0 ? D : 1) * 4, ctx->pool, st);
         if (e != cudaSuccess) {
             s->point_list = nullptr;
             return fail(gs_set_cuda_error(e, "cudaMallocAsync(point_list)", __FILE__, __LINE__));
@@ -517,7 +554,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
         s->D = D;
     }
     const bool fast = bin_fits_fast_path(max_count) && !(cfg->tuning & GS_TUNE_FORCE_RADIX_BINNING);
-    rc = ctx->sort.reserve(bin_scratch_bytes(c, D, fast), 1.25);
+    rc = ctx->sort.reserve(bin_scratch_bytes(c, D, fast), 1.25, ctx->pool, st);
     if (rc != GS_OK) return fail(rc);
     {
         StageTimer t(ctx, GS_STAGE_BIN_EMIT, st);
@@ -546,7 +583,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     // Depth-stratum boundaries for the coming speculative calls, from this call's depths (off this call's critical
     // path: queued behind the compositor).  STRATA_OFF is sticky for the shape.
     if (fast && ctx->spec.sub_cap > 0 && ctx->spec.strata_state != STRATA_OFF && !(cfg->tuning & GS_TUNE_NO_STRATA) && n > 0) {
-        rc = ctx->strata.reserve(bin_strata_bytes(c), 1.0);
+        rc = ctx->strata.reserve(bin_strata_bytes(c), 1.0, ctx->pool, st);
         if (rc != GS_OK) return fail(rc);
         rc = bin_learn_strata(c, rects, s->rec2, ctx->strata.p, st);
         if (rc != GS_OK) return fail(rc);
@@ -561,6 +598,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     ctx->stats.num_rendered = D;
     ctx->stats.num_visible = -1;
     ctx->stats.saved_bytes = (int64_t)(s->bytes + (size_t)(D > 0 ? D : 1) * 4);
+    pool_follow(ctx, (size_t)ctx->stats.saved_bytes);
     if (saved_out) {
         *saved_out = s;
     } else {
@@ -584,7 +622,7 @@ extern "C" int gs_backward(GsContext *ctx, const GsConfig *cfg, const GsInputs *
     const size_t n = (size_t)c.V * c.P;
     if (n == 0) return GS_OK;
 
-    rc = ctx->per_gaussian.reserve(n * GS_ACC_STRIDE * 4, 1.0);
+    rc = ctx->per_gaussian.reserve(n * GS_ACC_STRIDE * 4, 1.0, ctx->pool, st);
     if (rc != GS_OK) return rc;
     float *acc = static_cast<float *>(ctx->per_gaussian.p);
     {

@@ -11,7 +11,9 @@ behaviour; PyTorch is used for device memory, streams and autograd plumbing only
 """
 from __future__ import annotations
 
+import atexit
 import ctypes
+import threading
 from typing import NamedTuple, Optional
 
 import torch
@@ -40,16 +42,59 @@ class GaussianRasterizationSettings(NamedTuple):
 # contexts: one GsContext per (device, stream)
 # ---------------------------------------------------------------------------------------------------------
 _contexts: dict[tuple[int, int], ctypes.c_void_p] = {}
+_locks: dict[tuple[int, int], threading.RLock] = {}
+_registry_lock = threading.Lock()
+
+
+def _key(device: torch.device, stream_ptr: int) -> tuple[int, int]:
+    return (device.index if device.index is not None else torch.cuda.current_device(), stream_ptr)
 
 
 def _context(device: torch.device, stream_ptr: int) -> ctypes.c_void_p:
-    key = (device.index if device.index is not None else torch.cuda.current_device(), stream_ptr)
-    ctx = _contexts.get(key)
-    if ctx is None:
-        ctx = ctypes.c_void_p()
-        _capi.check(_capi.lib().gs_context_create(ctypes.byref(ctx)))
-        _contexts[key] = ctx
+    key = _key(device, stream_ptr)
+    with _registry_lock:
+        ctx = _contexts.get(key)
+        if ctx is None:
+            ctx = ctypes.c_void_p()
+            _capi.check(_capi.lib().gs_context_create(ctypes.byref(ctx)))
+            _contexts[key] = ctx
+            _locks[key] = threading.RLock()
     return ctx
+
+
+def _context_lock(device: torch.device, stream_ptr: int) -> threading.RLock:
+    """A GsContext serves one call at a time (include/gsplat_b200.h): the forward of one thread and the backward the
+    autograd engine runs on another take this lock around their gs_* calls."""
+    _context(device, stream_ptr)
+    return _locks[_key(device, stream_ptr)]
+
+
+def trim_memory(device=None) -> None:
+    """Hands the cached blocks of every context's private memory pool on `device` (all devices if None) back to the
+    driver -- the counterpart of torch.cuda.empty_cache() for the memory this library holds outside torch's allocator."""
+    with _registry_lock:
+        items = list(_contexts.items())
+    for (dev_index, _), ctx in items:
+        if device is None or torch.device(device).index in (None, dev_index):
+            with torch.cuda.device(dev_index):
+                _capi.check(_capi.lib().gs_context_trim(ctx))
+
+
+def destroy_contexts() -> None:
+    """Destroys every cached GsContext (registered with atexit; also usable from tests)."""
+    with _registry_lock:
+        items = list(_contexts.items())
+        _contexts.clear()
+        _locks.clear()
+    for (dev_index, _), ctx in items:
+        try:
+            with torch.cuda.device(dev_index):
+                _capi.lib().gs_context_destroy(ctx)
+        except Exception:
+            pass
+
+
+atexit.register(destroy_contexts)
 
 
 def current_context(device=None) -> ctypes.c_void_p:
@@ -175,13 +220,20 @@ class _RasterizeBatch(torch.autograd.Function):
             needs_grad = any(t is not None and t.requires_grad for t in
                              (means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp))
             saved = ctypes.c_void_p()
-            rc = _capi.lib().gs_forward(gctx, ctypes.byref(cfg), ctypes.byref(gin), ctypes.byref(gout),
-                                        ctypes.byref(saved) if needs_grad else None, stream_ptr)
-            _capi.check(rc)
+            with _context_lock(dev, stream_ptr):
+                rc = _capi.lib().gs_forward(gctx, ctypes.byref(cfg), ctypes.byref(gin), ctypes.byref(gout),
+                                            ctypes.byref(saved) if needs_grad else None, stream_ptr)
+                _capi.check(rc)
         if needs_grad:
             ctx.handle = _SavedHandle(gctx, saved, stream_ptr, dev)
             ctx.bs = bs
             ctx.ins = ins            # contiguous fp32 inputs the backward kernels re-read
+            # `ins` aliases the caller's tensors when they already are fp32-contiguous; autograd's own version check is
+            # bypassed for them, so do it by hand: an in-place update between forward and backward must raise, as it
+            # does with the reference op (which hands its inputs to save_for_backward)
+            srcs = {"means3D": means3D, "opacities": opacities, "shs": shs, "colors_precomp": colors_precomp,
+                    "scales": scales, "rotations": rotations, "cov3D_precomp": cov3D_precomp}
+            ctx.versions = [(k, t, t._version) for k, t in srcs.items() if t is not None]
             ctx.cfg_keep = keep
             ctx.dims = (S, P, V, M, H, W)
             ctx.want_means2D = means2D is not None and means2D.requires_grad
@@ -194,6 +246,10 @@ class _RasterizeBatch(torch.autograd.Function):
     def backward(ctx, grad_color, grad_radii=None, grad_depth=None):
         S, P, V, M, H, W = ctx.dims
         ins = ctx.ins
+        for name, t, version in ctx.versions:
+            if t._version != version:
+                raise RuntimeError(f"one of the variables needed for gradient computation has been modified by an inplace "
+                                   f"operation: {name} is at version {t._version}; expected version {version} instead")
         dev = ins["means3D"].device
         bs = ctx.bs
         keep: list = []
@@ -216,9 +272,10 @@ class _RasterizeBatch(torch.autograd.Function):
                 "dL_dcov3D": e(S, P, 6) if ins["cov3D_precomp"] is not None else None,
             }
             ig = GsInGrads(**{k: _ptr(t) for k, t in g.items()})
-            rc = _capi.lib().gs_backward(gctx, ctypes.byref(cfg), ctypes.byref(gin), ctx.handle.ptr, ctypes.byref(og),
-                                         ctypes.byref(ig), stream_ptr)
-            _capi.check(rc)
+            with _context_lock(dev, stream_ptr):
+                rc = _capi.lib().gs_backward(gctx, ctypes.byref(cfg), ctypes.byref(gin), ctx.handle.ptr, ctypes.byref(og),
+                                             ctypes.byref(ig), stream_ptr)
+                _capi.check(rc)
         return (g["dL_dmeans3D"], g["dL_dmeans2D"], g["dL_dshs"], g["dL_dcolors"], g["dL_dopacities"],
                 g["dL_dscales"], g["dL_drotations"], g["dL_dcov3D"], None)
 
@@ -271,8 +328,9 @@ class GaussianRasterizer(nn.Module):
                 cfg = _make_config(self._batch_settings(dev), 1, P, 0, keep)
                 pos = _f32c(positions)
                 present = torch.empty((P,), dtype=torch.uint8, device=dev)
-                _capi.check(_capi.lib().gs_mark_visible(gctx, ctypes.byref(cfg), pos.data_ptr(), present.data_ptr(),
-                                                        stream_ptr))
+                with _context_lock(dev, stream_ptr):
+                    _capi.check(_capi.lib().gs_mark_visible(gctx, ctypes.byref(cfg), pos.data_ptr(), present.data_ptr(),
+                                                            stream_ptr))
             return present.bool()
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,

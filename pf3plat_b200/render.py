@@ -77,11 +77,19 @@ def decoder_forward(means, covariances, harmonics, opacities, extrinsics, intrin
                     background_color, depth_mode: Optional[str] = None):
     """`DecoderSplattingCUDA.forward` (decoder_splatting_cuda.py:35-67) without the v-fold repeat: Gaussians
     (b,g,...), cameras (b,v,...).  Returns (color (b,v,3,h,w), depth (b,v,h,w) or None).  depth_mode "depth" is
-    fused into the colour pass; the reference's other modes are served by `render_depth`."""
+    fused into the colour pass; the reference's other modes are served by `render_depth`.
+
+    Gradients: like the reference's colour pass, the fused pass gives the CAMERAS no gradient (the view matrices enter
+    the rasterizer detached on both sides, cuda_splatting.py:85-87 / make_view_batch) and routes dL/ddepth to the means
+    only.  The reference's depth pass, however, builds its fake colour z = (extrinsics^-1 @ mean).z in torch
+    (cuda_splatting.py:239-242), so its depth IS differentiable w.r.t. the extrinsics -- PF3plat trains with
+    depth_mode "depth" on predicted poses.  Whenever the extrinsics require grad, "depth" therefore takes the
+    reference's two-pass route (`render_depth`), which carries that gradient."""
     b, v = extrinsics.shape[:2]
     flat = lambda t: t.reshape(b * v, *t.shape[2:])
     bg = background_color.reshape(1, 3).expand(b * v, 3)
-    if depth_mode is None or depth_mode == "depth":
+    pose_grad = depth_mode == "depth" and extrinsics.requires_grad and torch.is_grad_enabled()
+    if (depth_mode is None or depth_mode == "depth") and not pose_grad:
         out = render_views(flat(extrinsics), flat(intrinsics), flat(near), flat(far), image_shape, bg, means,
                            covariances, harmonics, opacities, with_depth=depth_mode is not None)
         if depth_mode is None:
