@@ -15,6 +15,12 @@ Reported on ONE JSON line (see the task contract):
              stream, recorded by the library around each stage), against MEASURED_PEAKS.json's HBM GB/s
   cpu_baseline  the CPU oracle port (oracle/gs_oracle.c, OpenMP) timed on this box's host cores on a bounded
              sample (whole views of the same workload)
+  moving_cloud  the forward when the cloud MOVES every step (means jittered by ~1 px, 5 % of the Gaussians re-drawn): the
+             speculative bucket capacities are learned from the previous call, so this leg reports ms/step AND how often
+             the speculation overflowed and the call was redone exactly
+  c4         BASELINE.json configs[3] (2M Gaussians x 32 views x 512x512), the 32 views split over the N ranks (strong
+             scaling): ms/step, 512x512 views/s
+  parity     view 0 against the oracle: pixels over 1e-4, fragile fraction, worst non-fragile / fragile error (N = 1)
 `--impl reference` times that CPU port alone (the reference's rasterizer is an absent external CUDA extension
 and the reference has no CPU path of its own: SURVEY.md section 0).
 """
@@ -161,6 +167,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tuning", type=int, default=0, help="GS_TUNE_* flags (experiments)")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 (2M x 32 views x 512x512) strong-scaling block")
+    ap.add_argument("--no-moving", action="store_true", help="skip the moving-cloud leg")
     args = ap.parse_args()
     global P_GAUSS, VIEWS, HW, WORKLOAD
     P_GAUSS, VIEWS, HW, WORKLOAD = WORKLOADS[args.workload]
@@ -285,8 +293,79 @@ def main():
     launches_fwd = rasterizer.last_stats(dev)["kernel_launches"]   # of the last timed step (steady state)
     ms_e2e = timed(e2e, args.steps, args.warmup)
     ms_fb = timed(fwd_bwd, args.steps, args.warmup)
-    clocks = sampler.stop()   # covers the three timed loops (warm-ups included: the GPU is under the same load)
     stats_fb = rasterizer.last_stats(dev)
+
+    # ---- moving cloud: every step renders a different cloud (training moves the Gaussians between steps), so the bucket
+    # capacities learned from step k-1 meet the counts of step k.  Means are jittered by ~1 px (sigma = 1 px worth of
+    # camera-space x/y at the Gaussian's depth) and 5 % of the Gaussians are re-drawn somewhere else; all variants are
+    # built before the timed region, each step only picks the next one.
+    moving = None
+    if not args.no_moving:
+        g = torch.Generator(device="cpu").manual_seed(77 + rank)
+        nvar = min(args.steps + args.warmup, 32)
+        px_at_depth = (2.0 * (0.5 / 0.86) / HW)                     # camera-space x per pixel per unit depth
+        variants = []
+        base = sc.means
+        for k in range(nvar):
+            m = base + torch.randn(P_GAUSS, 3, generator=g) * (base[:, 2:3] * px_at_depth) * torch.tensor([1.0, 1.0, 0.0])
+            redraw = torch.rand(P_GAUSS, generator=g) < 0.05
+            m[redraw] = base[torch.randperm(P_GAUSS, generator=g)[: int(redraw.sum())]]
+            variants.append(m.reshape(1, P_GAUSS, 3).contiguous().to(dev))
+        state = {"k": 0, "overflows": 0, "calls": 0}
+
+        def fwd_moving():
+            with torch.no_grad():
+                rasterize_batch(bs, variants[state["k"] % nvar], d["opacities"], shs=d["shs"], cov3D_precomp=d["cov3D_precomp"])
+            state["k"] += 1
+            state["calls"] += 1
+            state["overflows"] += int(rasterizer.last_stats(dev)["speculative"] == 0)
+
+        fwd_moving(); fwd_moving(); fwd_moving()                    # exact -> trial -> steady state
+        state.update(overflows=0, calls=0)
+        ms_mov = timed(fwd_moving, args.steps, args.warmup)
+        moving = {"ms_per_step": ms_mov / args.steps, "value": gauss_per_step * args.steps / (ms_mov * 1e-3),
+                  "unit": "Gaussians/s", "overflow_rate": state["overflows"] / max(1, state["calls"]),
+                  "calls": state["calls"], "variants": nvar,
+                  "perturbation": "means jittered by N(0, 1 px) in x/y, 5 % of the Gaussians moved to another Gaussian's position, every step"}
+        del variants
+        fwd()    # back to the static cloud's capacities for the stage profile below
+        fwd()
+    clocks = sampler.stop()   # covers the timed loops (warm-ups included: the GPU is under the same load)
+
+    # ---- C4 (configs[3]): 2M Gaussians, 32 views of 512x512, the views split over the ranks (STRONG scaling) ----
+    c4 = None
+    if not args.no_c4 and args.workload == "c2" and 32 % world == 0:
+        P4, V4, HW4 = 2_000_000, 32, 512
+        mine4 = shard_views(V4, rank, world)
+        sc4 = make_scene(P4, len(mine4), HW4, HW4, seed=0, first_view=mine4[0], total_views=V4)
+        vb4 = make_view_batch(sc4.extrinsics, sc4.intrinsics, sc4.near, sc4.far, scale_invariant=True)
+        cv = sc4.covariances
+        d4 = {"means3D": sc4.means.reshape(1, P4, 3), "opacities": sc4.opacities.reshape(1, P4),
+              "shs": sc4.harmonics.permute(0, 2, 1).contiguous().reshape(1, P4, D_SH, 3),
+              "cov3D_precomp": torch.stack([cv[:, 0, 0], cv[:, 0, 1], cv[:, 0, 2], cv[:, 1, 1], cv[:, 1, 2], cv[:, 2, 2]],
+                                           -1).reshape(1, P4, 6)}
+        d4 = {k: v.contiguous().float().to(dev) for k, v in d4.items()}
+        bs4 = BatchSettings(image_height=HW4, image_width=HW4, viewmatrix=vb4.viewmatrix.to(dev), projmatrix=vb4.projmatrix.to(dev),
+                            campos=vb4.campos.to(dev), bg=sc4.background.to(dev), sh_degree=4, tanfov=vb4.tanfov.to(dev),
+                            tuning=args.tuning)
+        del sc4, cv
+
+        def fwd4():
+            with torch.no_grad():
+                return rasterize_batch(bs4, d4["means3D"], d4["opacities"], shs=d4["shs"], cov3D_precomp=d4["cov3D_precomp"])
+
+        steps4 = max(3, args.steps // 4)
+        ms4 = timed(fwd4, steps4, 3)
+        st4 = rasterizer.last_stats(dev)
+        c4 = {"workload": WORKLOADS["c4"][3], "scaling": "strong", "views_total": V4, "views_per_gpu": len(mine4),
+              "steps": steps4, "ms_per_step": ms4 / steps4, "views_per_sec_512": V4 * steps4 / (ms4 * 1e-3),
+              "gaussians_per_sec": P4 * V4 * steps4 / (ms4 * 1e-3), "tile_instances_rank0": st4["num_rendered"],
+              "speculative": st4["speculative"]}
+        del d4, bs4
+        torch.cuda.empty_cache()
+        rasterizer.trim_memory(dev)
+        fwd()
+        fwd()
 
     # per-stage device time (library-recorded CUDA events on the launch stream), separate pass
     rasterizer.set_profiling(True, dev)
@@ -307,6 +386,8 @@ def main():
         # CPU baseline on a bounded sample + the oracle's own D (upstream's 3-sigma-square definition)
         cpu = None
         D_ref_per_view = None
+        parity = None
+        c1 = None
         if not args.no_cpu_baseline and world == 1:   # contract: the CPU baseline leg runs at N = 1 only
             from oracle import gs_oracle
             from oracle.gs_oracle import OracleRender
@@ -319,10 +400,38 @@ def main():
                 st, kw = view_args(sc, v)
                 r = OracleRender(st, frag_rel=0, **kw)
                 Ds.append(r.num_rendered)
-                if v == 0:
-                    err = np.abs(color[0].cpu().numpy() - r.color).max()
                 r.close()
             D_ref_per_view = sum(Ds) / VIEWS
+            from tests.util import image_report, oracle_view
+            r0 = oracle_view(sc, 0)                      # default fragility band (1e-4 relative), as in the tests
+            parity = image_report(color[0], r0)
+            parity["view"] = 0
+            parity["tolerance"] = "1e-4 abs RGB on non-fragile pixels; fragile = an alpha>=1/255 / T<1e-4 / footprint decision within 1e-4 (relative) of its threshold in the oracle"
+            err = max(parity["max_err_nonfragile"], parity["max_err_fragile"])
+            r0.close()
+            # C1 (BASELINE.json configs[0]: 10k Gaussians, 1 view, 256x256): both CPU restatements, forward, same box
+            c1 = {}
+            try:
+                sc1 = make_scene(10_000, 1, 256, 256, seed=0)
+                st1, kw1 = view_args(sc1, 0)
+                OracleRender(st1, frag_rel=0, **kw1).close()
+                t0 = time.perf_counter()
+                for _ in range(5):
+                    OracleRender(st1, frag_rel=0, **kw1).close()
+                c1["c_oracle_ms"] = 1e3 * (time.perf_counter() - t0) / 5
+                from oracle import torch_oracle
+                torch.set_num_threads(cores)
+                tk = {k: torch.from_numpy(np.ascontiguousarray(v)).float() for k, v in kw1.items()}
+                with torch.no_grad():
+                    t0 = time.perf_counter()
+                    torch_oracle.render(st1, dtype=torch.float32, **tk)
+                    c1["torch_oracle_ms"] = 1e3 * (time.perf_counter() - t0)
+                c1["workload"] = "C1: 10k Gaussians x 1 view x 256x256, forward"
+                c1["cores"] = cores
+                c1["c_oracle_gaussians_per_sec"] = 10_000 / (c1["c_oracle_ms"] * 1e-3)
+                c1["torch_oracle_gaussians_per_sec"] = 10_000 / (c1["torch_oracle_ms"] * 1e-3)
+            except Exception as exc:  # noqa: BLE001
+                c1["error"] = repr(exc)
             # (2) timed in a process of its own -- the same code as `--impl reference` -- so that this process's CUDA
             #     context, pinned buffers and thread pools do not perturb the CPU number (in-process it came out ~2.7x
             #     lower than the reference arm on the same box)
@@ -338,7 +447,7 @@ def main():
                 cpu = {"value": ref["value"], "unit": "Gaussians/s", "cores": ref["cpu_baseline"]["cores"], "kind": "port",
                        "sample": f"{nsteps} views ({P_GAUSS} Gaussians, {HW}x{HW}) of this workload, forward, "
                                  "oracle/gs_oracle.c with OpenMP, timed in a separate process (= bench.py --impl reference)",
-                       "max_abs_rgb_err_view0": float(err)}
+                       "max_abs_rgb_err_view0": float(err), "c1": c1}
             except Exception as exc:  # noqa: BLE001 -- fall back to timing it here
                 sys.stderr.write(f"cpu_baseline subprocess failed ({exc}); timing in-process\n")
             if cpu is None:
@@ -349,10 +458,12 @@ def main():
                 dt = time.perf_counter() - t0
                 cpu = {"value": P_GAUSS * VIEWS / dt, "unit": "Gaussians/s", "cores": cores, "kind": "port",
                        "sample": f"{VIEWS} views ({P_GAUSS} Gaussians, {HW}x{HW}), forward, oracle/gs_oracle.c with OpenMP, in-process",
-                       "max_abs_rgb_err_view0": float(err)}
-        # algorithmic bytes; D = upstream-definition tile instances when the oracle ran
+                       "max_abs_rgb_err_view0": float(err), "c1": c1}
+        # algorithmic bytes with the kernels' OWN tile-instance count D (the tight binning walks
+        # 27 % fewer instances than upstream's 3-sigma squares; using upstream's D would flatter every fraction)
         N = HW * HW
-        D_alg = (D_ref_per_view * VIEWS) if D_ref_per_view else D_ours
+        D_up = (D_ref_per_view * VIEWS) if D_ref_per_view else None
+        D_alg = D_ours
         S_sh = 12 * D_SH
         b_pre = 40 * P_GAUSS + S_sh * P_GAUSS + 48 * vis + 12 * P_GAUSS * VIEWS
         b_bin = 36 * D_alg
@@ -371,13 +482,41 @@ def main():
         sort_kernel = {0: "k_tile_sort", 1: "k_tile_sort_spec", 2: "k_stratum_sort"}[stats_fb["speculative"]]
         kern_ms = {"k_preprocess": stage.get("preprocess"), "k_emit_buckets": stage.get("bin_emit"),
                    sort_kernel: stage.get("bin_sort"), "k_composite_fwd": stage.get("composite")}
-        kern_bytes = {"k_preprocess": b_pre, "k_emit_buckets": 12 * D_alg, sort_kernel: 24 * D_alg, "k_composite_fwd": b_comp}
+        kern_bytes = {"k_preprocess": b_pre, "k_emit_buckets": 12 * D_alg, sort_kernel: 24 * D_alg, "k_composite_fwd": b_comp,
+                      # backward split of SURVEY 8(d)'s B_bwd: compositor = dL/dpixel + T + n_contrib, staged records,
+                      # per-(view,Gaussian) gradients written; preprocess backward = those re-read, inputs, outputs
+                      "k_composite_bwd": 20 * N * VIEWS + 40 * D_alg + 44 * vis,
+                      "k_preprocess_bwd": 88 * vis + 40 * P_GAUSS + S_sh * P_GAUSS + (40 + 12 * D_SH) * P_GAUSS}
         dom = max(kern_ms, key=lambda k: kern_ms[k] or 0)
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if os.path.exists(tpath) and args.workload == "c2":
-            traffic = json.load(open(tpath)).get(dom, {}).get("dram_bytes_per_launch")
+        # ncu-derived per-launch figures of the same workload (profiles/r2_traffic.json, made by scripts/ncu_summary.py):
+        # DRAM bytes and executed warp instructions.  The issue roofline is instructions / (SMs x 4 schedulers x clock).
+        traffic, issue = None, None
+        prof = {}
+        for name in ("r2_traffic.json", "r1_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(tpath) and args.workload == "c2":
+                prof = json.load(open(tpath))
+                break
+        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+        clock_hz = (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0) * 1e6
+
+        def issue_roofline(kernel, ms):
+            winst = prof.get(kernel, {}).get("warp_instructions_per_launch") or prof.get(kernel, {}).get("warp_instructions")
+            if not winst or not ms:
+                return None
+            floor_ms = winst / (sm_count * 4 * clock_hz) * 1e3
+            return {"warp_instructions_per_launch": winst, "issue_slots_per_s": sm_count * 4 * clock_hz,
+                    "floor_ms": floor_ms, "frac": floor_ms / ms,
+                    "source": "ncu smsp__inst_executed.sum of this workload (profiles/), clock sampled in this run"}
+
+        traffic = prof.get(dom, {}).get("dram_bytes_per_launch")
+        issue = issue_roofline(dom, kern_ms[dom])
         dom_gbs = kern_bytes[dom] / (kern_ms[dom] * 1e-3) / 1e9
+        issue_bound = dom in ("k_composite_fwd",) or (issue is not None and issue["frac"] > dom_gbs / hbm)
+        bwd_kernels = {"k_composite_bwd": stage.get("composite_bwd"), "k_preprocess_bwd": stage.get("preprocess_bwd")}
+        kernels_report = {k: {"ms": v, "hbm_frac": (kern_bytes[k] / (v * 1e-3) / 1e9 / hbm) if (v and k in kern_bytes) else None,
+                              "issue": issue_roofline(k, v), "dram_bytes_per_launch": prof.get(k, {}).get("dram_bytes_per_launch")}
+                          for k, v in {**kern_ms, **bwd_kernels}.items() if v}
         line = {
             "metric": "gaussians_per_sec_fwd_256", "value": gauss_per_step * args.steps / (ms_fwd * 1e-3),
             "unit": "Gaussians/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -393,19 +532,25 @@ def main():
             "fwd_bwd": {"value": gauss_per_step * args.steps / (ms_fb * 1e-3), "unit": "Gaussians/s",
                         "ms_per_step": ms_fb / args.steps, "loss": "MSE to U(0,1) target"},
             "gpu_launches": (launches_fwd) * args.steps,
-            "gpu_launches_note": f"{launches_fwd} own kernels per forward step (k_preprocess, k_spec_check, "
-                                 f"k_tile_sort_spec, k_composite_fwd in steady state); fwd+bwd step: "
-                                 f"{stats_fb['kernel_launches']}",
-            "roofline": {"kernel": dom, "bound": "hbm", "achieved": dom_gbs, "peak": hbm, "unit": "GB/s",
-                         "frac": dom_gbs / hbm, "traffic": traffic, "peak_source": hbm_src,
+            "gpu_launches_note": f"{launches_fwd} own kernels per forward step (k_preprocess, the tile sort, "
+                                 f"k_composite_fwd in steady state); fwd+bwd step: {stats_fb['kernel_launches']}",
+            "roofline": {"kernel": dom, "bound": "issue" if issue_bound else "hbm", "achieved": dom_gbs, "peak": hbm,
+                         "unit": "GB/s", "frac": dom_gbs / hbm, "traffic": traffic, "peak_source": hbm_src,
                          "algorithmic_bytes_per_launch": kern_bytes[dom], "ms_per_launch": kern_ms[dom],
-                         "note": "the compositors are instruction-issue bound (ncu: issue slots ~75 % busy, DRAM < 10 %); "
-                                 "their HBM fraction is low by nature (DESIGN.md sections 5.3, 6)"},
+                         "issue": issue,
+                         "note": "achieved/peak/frac are the HBM figures the contract asks for, computed with the kernel's own "
+                                 "tile-instance count; `bound` names what really limits the kernel: the compositors are "
+                                 "instruction-issue bound (issue.frac = executed warp instructions / issue slots available in "
+                                 "the measured time; DRAM < 15 % of peak)"},
+            "kernels": kernels_report,
+            "parity": parity,
+            "moving_cloud": moving,
+            "c4": c4,
             "roofline_stages": stages,
             "roofline_forward": {"bytes": b_fwd, "achieved_gbs": b_fwd / (ms_fwd / args.steps * 1e-3) / 1e9,
                                  "frac": b_fwd / (ms_fwd / args.steps * 1e-3) / 1e9 / hbm},
             "stage_ms": stage,
-            "tile_instances": {"ours_tight": D_ours, "upstream_definition": D_alg, "visible": vis},
+            "tile_instances": {"ours_tight": D_ours, "upstream_definition": D_up, "visible": vis},
             "cpu_baseline": cpu,
             "clocks": clocks,
             "psnr_vs_target_mean": float(psnr.mean().item()),

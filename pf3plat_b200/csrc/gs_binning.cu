@@ -111,15 +111,19 @@ __global__ void k_emit_buckets(const DevCfg c, const float4 *__restrict__ rec0, 
     // that several round trips to L2 are in flight per thread (the kernel is latency-bound: 16 % of issue slots busy).
     constexpr int BATCH = 4;
     const int w = r.z - r.x, nt = w * (r.w - r.y);
+    int cx = r.x, cy = r.y;  // row-major walk of the rectangle (no integer division per candidate)
     for (int t0 = 0; t0 < nt; t0 += BATCH) {
         size_t slot[BATCH];
         uint32_t pos[BATCH];
         bool ok[BATCH];
 #pragma unroll
         for (int k = 0; k < BATCH; k++) {
-            const int t = t0 + k, ty = r.y + t / w, tx = r.x + t - (t / w) * w;
-            ok[k] = t < nt && gs_tile_reached(q0, q1, q2, tx, ty);  // same predicate as the count in k_preprocess
-            slot[k] = (size_t)(tbase + (uint32_t)(ty * c.gx + tx)) * BIN_SUB + sub;
+            ok[k] = cy < (int)r.w && gs_tile_reached(q0, q1, q2, cx, cy);  // same predicate as the count in k_preprocess
+            slot[k] = (size_t)(tbase + (uint32_t)(cy * c.gx + cx)) * BIN_SUB + sub;
+            if (++cx == (int)r.z) {
+                cx = r.x;
+                cy++;
+            }
         }
 #pragma unroll
         for (int k = 0; k < BATCH; k++)

@@ -188,6 +188,7 @@ size_t saved_layout(GsSaved *s, const DevCfg &c, unsigned char *base) {
     s->ranges = reinterpret_cast<uint2 *>(take((size_t)c.V * c.ntiles * 8));
     s->final_T = reinterpret_cast<float *>(take(px * 4));
     s->n_contrib = reinterpret_cast<uint32_t *>(take(px * 4));
+    s->sched = reinterpret_cast<uint32_t *>(take(8));
     return off;
 }
 
@@ -466,7 +467,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
         }
         {
             StageTimer t(ctx, GS_STAGE_COMPOSITE, st);
-            rc = launch_composite_fwd(c, *s, out->color, out->depth, st);
+            rc = launch_composite_fwd(c, *s, out->color, out->depth, st, (cfg->tuning & GS_TUNE_FWD_V1) ? 1 : 0);
             if (rc != GS_OK) return fail(rc);
         }
         e = cudaEventSynchronize(ctx->ev_info);  // the one host sync of the forward (verification only)
@@ -575,7 +576,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
 
     {
         StageTimer t(ctx, GS_STAGE_COMPOSITE, st);
-        rc = launch_composite_fwd(c, *s, out->color, out->depth, st);
+        rc = launch_composite_fwd(c, *s, out->color, out->depth, st, (cfg->tuning & GS_TUNE_FWD_V1) ? 1 : 0);
         if (rc != GS_OK) return fail(rc);
         ctx->stats.kernel_launches += 1;
     }

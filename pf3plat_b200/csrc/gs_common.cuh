@@ -41,6 +41,7 @@ struct GsSaved {
     uint2 *ranges;                // [V*ntiles] [start,end) into point_list
     float *final_T;               // [V*H*W]
     uint32_t *n_contrib;          // [V*H*W] 1-based list position of the last contributor
+    uint32_t *sched;              // [2] work counter of the persistent compositor (zeroed by its launcher)
     int64_t D;
     int P, S, V, H, W;
     uint32_t flags;
@@ -101,7 +102,8 @@ int bin_sort_fallback(const DevCfg &c, int64_t D, const float4 *rec0, const floa
                       const ushort4 *rects, void *scratch, size_t scratch_bytes, uint32_t *point_list, uint2 *ranges,
                       cudaStream_t st);
 
-int launch_composite_fwd(const DevCfg &c, const GsSaved &s, float *color, float *depth, cudaStream_t st);
+int launch_composite_fwd(const DevCfg &c, const GsSaved &s, float *color, float *depth, cudaStream_t st,
+                         int variant = 0 /* 1: the round-1 kernel, one CTA per tile (GS_TUNE_FWD_V1) */);
 int launch_composite_bwd(const DevCfg &c, const GsSaved &s, const float *dL_dcolor, const float *dL_ddepth,
                          float *grad_acc /* [V*P*GS_ACC_STRIDE], zeroed */, cudaStream_t st,
                          int variant = 0 /* 1: the round-1 kernel (GS_TUNE_BWD_V1) */);
@@ -288,6 +290,14 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// the mbarrier receives one arrival from this thread once all cp.async copies it has issued so far have landed
+// (the barrier's expected count must already include that arrival: .noinc)
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
     asm volatile(

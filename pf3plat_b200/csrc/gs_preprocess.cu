@@ -242,14 +242,20 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
                     // samples when the store followed its atomic directly).  Candidates go EMIT_BATCH at a time,
                     // all their atomics in flight together, and the dependent stores are deferred until the next batch
                     // is about to be issued -- normally one whole view of arithmetic later.
+                    // candidates in row-major order of the rectangle; (cx, cy) walks it without the integer division
+                    // that t / w cost per candidate (the emission loop was 36 % of this kernel's instructions)
+                    int cx = sp.rect.x, cy = sp.rect.y;
                     for (int t0 = 0; t0 < nt; t0 += EMIT_BATCH) {
                         bool ok[EMIT_BATCH];
                         uint32_t slot[EMIT_BATCH];
 #pragma unroll
                         for (int k = 0; k < EMIT_BATCH; k++) {
-                            const int t = t0 + k, ty = sp.rect.y + t / w, tx = sp.rect.x + t - (t / w) * w;
-                            ok[k] = t < nt && gs_tile_reached(sp.r0, sp.r1, sp.r2, tx, ty);
-                            slot[k] = (tbase + (uint32_t)(ty * c.gx + tx)) * BIN_SUB + sub;
+                            ok[k] = cy < (int)sp.rect.w && gs_tile_reached(sp.r0, sp.r1, sp.r2, cx, cy);
+                            slot[k] = (tbase + (uint32_t)(cy * c.gx + cx)) * BIN_SUB + sub;
+                            if (++cx == (int)sp.rect.z) {
+                                cx = sp.rect.x;
+                                cy++;
+                            }
                         }
                         flush_pending();
                         pend_key = ((uint64_t)__float_as_uint(sp.r2.y) << 32) | (uint32_t)i;
@@ -261,11 +267,10 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
                         }
                     }
                 } else {
-                    for (int t = 0; t < nt; t++) {
-                        const int ty = sp.rect.y + t / w, tx = sp.rect.x + t - (t / w) * w;
-                        if (gs_tile_reached(sp.r0, sp.r1, sp.r2, tx, ty))
-                            atomicAdd(&emit.counters[(size_t)((tbase + (uint32_t)(ty * c.gx + tx)) * BIN_SUB + sub) * BIN_PAD], 1u);
-                    }
+                    for (int ty = sp.rect.y; ty < (int)sp.rect.w; ty++)
+                        for (int tx = sp.rect.x; tx < (int)sp.rect.z; tx++)
+                            if (gs_tile_reached(sp.r0, sp.r1, sp.r2, tx, ty))
+                                atomicAdd(&emit.counters[(size_t)((tbase + (uint32_t)(ty * c.gx + tx)) * BIN_SUB + sub) * BIN_PAD], 1u);
                 }
             }
             meta[o] = (uint8_t)sp.meta;

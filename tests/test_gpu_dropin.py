@@ -75,6 +75,57 @@ def test_gradients_flow_to_the_encoder_side_tensors():
         assert err <= 1e-3, float(err)
 
 
+def test_depth_gradient_reaches_the_extrinsics_like_the_reference():
+    """PF3plat trains with depth_mode "depth" on PREDICTED poses (config/main.yaml:50): the reference's depth pass builds
+    z = (extrinsics^-1 @ mean).z in torch (cuda_splatting.py:239-242), so a depth loss reaches the extrinsics.  The fused
+    colour+depth pass cannot carry that gradient (cameras enter the kernels detached), so decoder_forward must take the
+    two-pass route whenever the extrinsics require grad -- and give the reference's gradient."""
+    from pf3plat_b200.render import decoder_forward
+    dev = torch.device("cuda:0")
+    b, v, hw = 1, 2, (32, 32)
+    scs, means, cov, sh, opac, ext, intr, nr, fr = _scenes(dev, b, v, P=1500, hw=hw)
+    bg = torch.zeros(3, device=dev)
+    w = torch.rand(b, v, *hw, device=dev)
+    ext_a = ext.clone().requires_grad_(True)
+    means_a = means.clone().requires_grad_(True)
+    color, depth = decoder_forward(means_a, cov, sh, opac, ext_a, intr, nr, fr, hw, bg, depth_mode="depth")
+    (depth * w).sum().backward()
+    ext_r = ext.clone().requires_grad_(True)
+    means_r = means.clone().requires_grad_(True)
+    flat = lambda t: t.reshape(b * v, *t.shape[2:])
+    rep = lambda t: t.repeat_interleave(v, dim=0)
+    rd = render_depth_like_reference(flat(ext_r), flat(intr), flat(nr), flat(fr), hw, rep(means_r), rep(cov), rep(opac))
+    (rd.reshape(b, v, *hw) * w).sum().backward()
+    assert ext_a.grad is not None and float(ext_r.grad.abs().max()) > 0
+    err = (ext_a.grad - ext_r.grad).abs().max() / ext_r.grad.abs().max()
+    assert err <= 1e-3, float(err)
+    err_m = (means_a.grad - means_r.grad).abs().max() / means_r.grad.abs().max()
+    assert err_m <= 1e-3, float(err_m)
+    # without a pose gradient the fused single pass is used and gives the same depth
+    with torch.no_grad():
+        _, depth_fused = decoder_forward(means, cov, sh, opac, ext, intr, nr, fr, hw, bg, depth_mode="depth")
+    assert (depth_fused - depth.detach()).abs().max() <= 2e-3 * float(depth.abs().max())
+
+
+def test_inplace_update_between_forward_and_backward_raises_and_pool_trims():
+    from pf3plat_b200.rasterizer import last_stats, trim_memory
+    from pf3plat_b200.render import render_views
+    dev = torch.device("cuda:0")
+    sc = make_scene(2000, 1, 32, 32, seed=6).to(dev)
+    means = sc.means[None].clone().requires_grad_(True)
+    color = render_views(sc.extrinsics, sc.intrinsics, sc.near, sc.far, (32, 32), sc.background, means,
+                         sc.covariances[None], sc.harmonics[None], sc.opacities[None])
+    with torch.no_grad():
+        means.mul_(1.0)      # an optimizer step / clamp_ on a leaf between forward and backward
+    with pytest.raises(RuntimeError, match="modified by an inplace operation"):
+        color.sum().backward()
+    del color
+    trim_memory(dev)         # the library's private pool gives its cached blocks back; next call still works
+    again = render_views(sc.extrinsics, sc.intrinsics, sc.near, sc.far, (32, 32), sc.background, sc.means[None],
+                         sc.covariances[None], sc.harmonics[None], sc.opacities[None])
+    assert torch.isfinite(again).all() and last_stats(dev)["num_rendered"] > 0
+
+
 def test_orthographic_style_settings_with_tensor_tanfov():
     """render_cuda_orthographic passes tanfovx/tanfovy as 0-dim CUDA tensors (cuda_splatting.py:195-196)."""
     from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer

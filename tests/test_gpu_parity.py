@@ -223,6 +223,43 @@ def _render_with_tuning(sc, dev, tuning):
     return color, last_stats(dev)
 
 
+def test_compositor_variants_agree():
+    """Round-2 kernels against the round-1 kernels they replace (kept behind tuning flags for A/B): the persistent
+    warp-specialised forward compositor gives bit-identical images, final T and contributor counts (same arithmetic in
+    the same order); the pair-matrix backward gives the same gradients up to the re-association of the sums."""
+    from pf3plat_b200._capi import GS_TUNE_BWD_V1, GS_TUNE_FWD_V1
+    from pf3plat_b200.cameras import make_view_batch
+    from pf3plat_b200.rasterizer import BatchSettings, rasterize_batch
+    dev = _dev()
+    for sc, depth in ((make_scene(40000, 3, 80, 112, seed=12), True), (make_scene(300, 1, 16, 16, seed=13), False),
+                      (make_scene(150000, 2, 128, 128, seed=14), False)):
+        d = sc.to(dev)
+        vb = make_view_batch(d.extrinsics, d.intrinsics, d.near, d.far)
+        h, w = sc.image_shape
+        c = d.covariances
+        cov6 = torch.stack([c[:, 0, 0], c[:, 0, 1], c[:, 0, 2], c[:, 1, 1], c[:, 1, 2], c[:, 2, 2]], -1)[None]
+        bg = torch.rand(d.background.shape, device=dev)
+        outs, grads = {}, {}
+        for tuning in (0, GS_TUNE_FWD_V1, GS_TUNE_BWD_V1, GS_TUNE_FWD_V1 | GS_TUNE_BWD_V1):
+            bs = BatchSettings(image_height=h, image_width=w, viewmatrix=vb.viewmatrix, projmatrix=vb.projmatrix,
+                               campos=vb.campos, bg=bg, sh_degree=4, tanfov=vb.tanfov, view_scale=vb.scale,
+                               tuning=tuning, with_depth=depth)
+            leaves = [t.clone().requires_grad_(True) for t in (d.means[None], d.opacities[None],
+                                                               d.harmonics.permute(0, 2, 1).contiguous()[None], cov6)]
+            out = rasterize_batch(bs, leaves[0], leaves[1], shs=leaves[2], cov3D_precomp=leaves[3])
+            g = torch.Generator(device="cpu").manual_seed(3)
+            wgt = torch.randn(out[0].shape, generator=g).to(dev)
+            loss = (out[0] * wgt).sum() + (0.01 * out[2].sum() if depth else 0.0)
+            loss.backward()
+            outs[tuning] = [o.detach() for o in out]
+            grads[tuning] = [t.grad for t in leaves]
+        for tuning in (GS_TUNE_FWD_V1, GS_TUNE_BWD_V1, GS_TUNE_FWD_V1 | GS_TUNE_BWD_V1):
+            for a, b in zip(outs[0], outs[tuning]):
+                assert torch.equal(a, b), tuning
+            for a, b in zip(grads[0], grads[tuning]):
+                assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max()) + 1e-12, tuning
+
+
 def test_binning_paths_agree_bit_for_bit():
     """Exact-capacity buckets, speculative-capacity buckets (later calls of a shape; whole-tile sorts or depth strata)
     and the device-wide radix-sort fallback give the same lists, hence the same pixels; overflowing the learned
