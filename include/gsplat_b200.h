@@ -63,6 +63,7 @@ enum {
     GS_TUNE_NO_STRATA = 8u,           /* speculative path: never bin by depth stratum (whole-tile sorts only) */
     GS_TUNE_BWD_V1 = 16u,             /* backward compositor: the round-1 kernel (per-pixel 10-component gradients + transpose-reduce) instead of the pair-matrix kernel (A/B) */
     GS_TUNE_FWD_V1 = 32u,             /* forward compositor: the round-1 kernel (one CTA per tile, all-thread cp.async staging, CTA barriers) instead of the persistent warp-specialised kernel (A/B) */
+    GS_TUNE_STRATA_MERGE_SORT = 64u,  /* stratified binning: sort the strata with the round-1 cub::BlockMergeSort kernel instead of the hand-written warp-per-stratum distribution sort (A/B) */
     GS_TUNE_FEED_PIECES_SHIFT = 8     /* gs_render_host: bits 8..11 = pieces the SH block is copied in (0 default, 1 = one plain copy) */
 };
 

@@ -511,6 +511,168 @@ k_stratum_sort(uint32_t nvt, uint32_t sub_cap, const uint32_t *__restrict__ curs
     else sort_bucket_merge<THREADS, 1>(load, dst, n, ts_smem);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Hand-written stratum sort (round 2): ONE WARP per stratum, no CTA barrier, no library primitive.
+// cub::BlockMergeSort spent 5 760 warp-instructions per ~410-key stratum at 50 % issue utilisation (seven merge rounds
+// of binary searches, two CTA barriers each).  A stratum is small and its depths are spread over a narrow, roughly
+// uniform range, so one distribution pass nearly sorts it:
+//   1. warp min / max of the depth bits (REDUX);
+//   2. 32 depth buckets, bucket = floor((bits - min) * 32 / (range + 1)) -- monotone in the key, so sorted buckets
+//      concatenate to the sorted stratum.  Counting is ATOMIC-FREE: five ballots of the bucket number's bits give every
+//      lane L the mask of the round's keys that fall into bucket L (lane L keeps bucket L's count in a register);
+//   3. a warp scan turns counts into bucket offsets; a second sweep of the same ballots scatters the keys to their
+//      bucket in shared memory (position = bucket cursor + rank among the round's equal-bucket lanes);
+//   4. lane L insertion-sorts bucket L (~13 keys) on the full 64-bit (depth, index) key -- index ties included;
+//   5. the indices leave with coalesced stores.
+// A bucket of more than 32 keys (depth ties en masse: all depths equal -> buckets are formed on the index instead;
+// anything else that crowds) is ranked by the whole warp cooperatively and written straight to its final place: always
+// correct, only slower.  ~1 400 warp-instructions per stratum.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int RS_WARPS = 4;          // strata per CTA (independent warps)
+constexpr uint32_t RS_BIG = 32;      // buckets longer than this are ranked cooperatively
+constexpr uint32_t RS_DONE = 0x80000000u;  // marks keys whose index has already been written (indices are < 2^31)
+
+__global__ void __launch_bounds__(RS_WARPS * 32)
+k_stratum_rank_sort(uint32_t nvt, uint32_t sub_cap, uint32_t cap_pad, const uint32_t *__restrict__ cursor,
+                    const uint64_t *__restrict__ bucket, uint32_t *__restrict__ point_list, uint2 *__restrict__ ranges,
+                    uint32_t *__restrict__ acc, uint32_t *__restrict__ info) {
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sidx = blockIdx.x * RS_WARPS + warp;   // (view, tile, stratum)
+    if (sidx >= nvt * BIN_SUB) return;
+    const uint32_t vt = sidx / BIN_SUB, k = sidx % BIN_SUB;
+    // the tile's eight cursors: clamped counts, this stratum's offset inside the tile's list, the verdict's sums
+    const uint32_t raw = lane < BIN_SUB ? cursor[((size_t)vt * BIN_SUB + lane) * BIN_PAD] : 0u;
+    const uint32_t cnt = min(raw, sub_cap);  // clamped: an overflowed call is redone
+    const uint32_t total = __reduce_add_sync(0xffffffffu, cnt);
+    const uint32_t below = __reduce_add_sync(0xffffffffu, lane < k ? cnt : 0u);
+    const uint32_t n = __shfl_sync(0xffffffffu, cnt, k);
+    const uint32_t base = vt * BIN_SUB * sub_cap;
+    if (k == 0) {
+        const uint32_t raw_total = __reduce_add_sync(0xffffffffu, raw), raw_max = __reduce_max_sync(0xffffffffu, raw);
+        if (lane == 0) {
+            ranges[vt] = make_uint2(base, base + total);
+            atomicAdd(&acc[0], raw_total);
+            atomicMax(&acc[1], raw_total);
+            atomicMax(&acc[2], raw_max);
+            if (raw_max > sub_cap) atomicOr(&acc[3], 1u);
+            __threadfence();
+            if (atomicAdd(&acc[4], 1u) == nvt - 1) {  // every tile has been accounted for
+                __threadfence();
+                info[0] = atomicAdd(&acc[0], 0u);
+                info[1] = atomicAdd(&acc[1], 0u);
+                info[2] = atomicAdd(&acc[2], 0u);
+                info[3] = atomicAdd(&acc[3], 0u);  // the host reads them after an event recorded behind this kernel
+            }
+        }
+    }
+    if (n == 0) return;
+    const uint64_t *__restrict__ src = bucket + (size_t)sidx * sub_cap;
+    uint64_t *srt = reinterpret_cast<uint64_t *>(rs_smem) + (size_t)warp * cap_pad;
+    uint32_t *dst = point_list + base + below;
+
+    // 1. range of the depth bits (positive floats order like their bit patterns)
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    for (uint32_t i = lane; i < n; i += 32) {
+        const uint32_t d = (uint32_t)(src[i] >> 32);
+        lo = min(lo, d);
+        hi = max(hi, d);
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    const bool by_index = lo == hi;  // every depth equal: spread the keys by their index instead
+    if (by_index) {
+        lo = 0xffffffffu, hi = 0u;
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint32_t d = (uint32_t)src[i];
+            lo = min(lo, d);
+            hi = max(hi, d);
+        }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+    }
+    const float scale = 32.0f / ((float)(hi - lo) + 1.0f);
+    auto bucket_of = [&](uint64_t key) -> uint32_t {  // monotone in the key: int -> float -> int conversions all are
+        const uint32_t x = by_index ? (uint32_t)key : (uint32_t)(key >> 32);
+        return min(31u, (uint32_t)(__uint2float_rz(x - lo) * scale));
+    };
+    // mask of the round's lanes whose key falls into bucket `lane`, from the ballots of the bucket number's five bits
+    const uint32_t x0 = (lane & 1u) ? 0u : ~0u, x1 = (lane & 2u) ? 0u : ~0u, x2 = (lane & 4u) ? 0u : ~0u,
+                   x3 = (lane & 8u) ? 0u : ~0u, x4 = (lane & 16u) ? 0u : ~0u;
+    auto mine_mask = [&](uint32_t b, bool valid) -> uint32_t {
+        uint32_t m = __ballot_sync(0xffffffffu, valid);
+        m &= __ballot_sync(0xffffffffu, b & 1u) ^ x0;
+        m &= __ballot_sync(0xffffffffu, b & 2u) ^ x1;
+        m &= __ballot_sync(0xffffffffu, b & 4u) ^ x2;
+        m &= __ballot_sync(0xffffffffu, b & 8u) ^ x3;
+        m &= __ballot_sync(0xffffffffu, b & 16u) ^ x4;
+        return m;
+    };
+    // 2. count
+    uint32_t count = 0;
+    for (uint32_t r0 = 0; r0 < n; r0 += 32) {
+        const uint32_t i = r0 + lane;
+        const bool valid = i < n;
+        const uint32_t b = valid ? bucket_of(src[i]) : 0u;
+        count += __popc(mine_mask(b, valid));
+    }
+    // 3. offsets, scatter
+    uint32_t incl = count;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((int)lane >= d) incl += t;
+    }
+    const uint32_t start = incl - count;
+    uint32_t run = start;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (uint32_t r0 = 0; r0 < n; r0 += 32) {
+        const uint32_t i = r0 + lane;
+        const bool valid = i < n;
+        const uint64_t key = valid ? src[i] : 0ull;
+        const uint32_t b = valid ? bucket_of(key) : 0u;
+        const uint32_t m = mine_mask(b, valid);
+        const uint32_t same = __shfl_sync(0xffffffffu, m, b);     // the lanes whose key shares my bucket
+        const uint32_t at = __shfl_sync(0xffffffffu, run, b);     // that bucket's cursor
+        if (valid) srt[at + __popc(same & lt)] = key;
+        run += __popc(m);
+    }
+    __syncwarp();
+    // 4. sort inside the buckets
+    uint32_t big = __ballot_sync(0xffffffffu, count > RS_BIG);
+    if (count <= RS_BIG) {
+        for (uint32_t a = start + 1; a < start + count; a++) {
+            const uint64_t key = srt[a];
+            uint32_t j = a;
+            while (j > start && srt[j - 1] > key) {
+                srt[j] = srt[j - 1];
+                j--;
+            }
+            srt[j] = key;
+        }
+    }
+    while (big) {  // a crowded bucket: the whole warp ranks its keys and stores their indices directly
+        const int owner = __ffs(big) - 1;
+        big &= big - 1u;
+        const uint32_t bs = __shfl_sync(0xffffffffu, start, owner), bn = __shfl_sync(0xffffffffu, count, owner);
+        for (uint32_t e0 = 0; e0 < bn; e0 += 32) {
+            const uint32_t e = e0 + lane;
+            const uint64_t key = e < bn ? srt[bs + e] : 0ull;
+            uint32_t rank = 0;
+            for (uint32_t q = 0; q < bn; q++) rank += srt[bs + q] < key ? 1u : 0u;  // keys are distinct: (depth, index)
+            if (e < bn) dst[bs + rank] = (uint32_t)key;
+        }
+        __syncwarp();
+        for (uint32_t e = lane; e < bn; e += 32) srt[bs + e] |= RS_DONE;
+    }
+    __syncwarp();
+    // 5. out
+    for (uint32_t i = lane; i < n; i += 32) {
+        const uint32_t id = (uint32_t)srt[i];
+        if (!(id & RS_DONE)) dst[i] = id;
+    }
+}
+
 template <int THREADS, int MAX_ITEMS>
 int launch_stratum_sort(int nvt, uint32_t sub_cap, const uint32_t *cursor, const uint64_t *bucket, uint32_t *point_list,
                         uint2 *ranges, uint32_t *acc, uint32_t *info, cudaStream_t st) {
@@ -523,7 +685,24 @@ int launch_stratum_sort(int nvt, uint32_t sub_cap, const uint32_t *cursor, const
 }
 
 int bin_sort_strata(const DevCfg &c, uint32_t sub_cap, const uint32_t *cursor, const void *bucket, uint32_t *point_list,
-                    uint2 *ranges, uint32_t *acc, uint32_t *info, cudaStream_t st) {
+                    uint2 *ranges, uint32_t *acc, uint32_t *info, cudaStream_t st, bool merge_sort) {
+    if (!merge_sort) {
+        // hand-written warp-per-stratum distribution sort (default)
+        if (sub_cap > BIN_STRATUM_CAP) return gs_set_error(GS_ERR_INVALID, "stratum capacity beyond the sort's");
+        const uint32_t nvt = (uint32_t)c.V * (uint32_t)c.ntiles;
+        const uint32_t cap_pad = (sub_cap + 31u) & ~31u;
+        const size_t smem = (size_t)RS_WARPS * cap_pad * 8;
+        static size_t smem_set = 0;
+        if (smem > smem_set) {
+            GS_CUDA_OK(cudaFuncSetAttribute(k_stratum_rank_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_set = smem;
+        }
+        const uint32_t ctas = (nvt * BIN_SUB + RS_WARPS - 1) / RS_WARPS;
+        k_stratum_rank_sort<<<ctas, RS_WARPS * 32, smem, st>>>(nvt, sub_cap, cap_pad, cursor, static_cast<const uint64_t *>(bucket),
+                                                               point_list, ranges, acc, info);
+        GS_CUDA_OK(cudaGetLastError());
+        return GS_OK;
+    }
     // 128 threads: measured on C2 (sub-buckets of ~400 keys) 64 / 128 / 256 threads = 0.181 / 0.170 / 0.187 ms.
     // The kernel is instantiated for the call's capacity: the 4- and 8-keys-per-thread versions need fewer registers
     // and less shared memory than the 16-key one, i.e. more resident CTAs for this latency-bound sort.

@@ -455,7 +455,8 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
         {
             StageTimer t(ctx, GS_STAGE_BIN_SORT, st);
             if (strata) {
-                rc = bin_sort_strata(c, sub_cap, cursor, ctx->sort.p, s->point_list, s->ranges, verdict_acc, ctx->d_word, st);
+                rc = bin_sort_strata(c, sub_cap, cursor, ctx->sort.p, s->point_list, s->ranges, verdict_acc, ctx->d_word, st,
+                                     (cfg->tuning & GS_TUNE_STRATA_MERGE_SORT) != 0);
                 if (rc == GS_OK && (e = cudaEventRecord(ctx->ev_info, st)) != cudaSuccess)
                     return fail(gs_set_cuda_error(e, "read back binning info", __FILE__, __LINE__));
                 if (rc == GS_OK && (e = start_radii_copy()) != cudaSuccess)

@@ -91,7 +91,8 @@ int bin_sort_fast(const DevCfg &c, uint32_t max_count, const uint32_t *tile_star
 int bin_spec_check(const DevCfg &c, uint32_t sub_cap, uint32_t tile_limit, const uint32_t *cursor, uint32_t *info,
                    cudaStream_t st);
 int bin_sort_strata(const DevCfg &c, uint32_t sub_cap, const uint32_t *cursor, const void *bucket, uint32_t *point_list,
-                    uint2 *ranges, uint32_t *acc /* 8 zeroed words */, uint32_t *info, cudaStream_t st);
+                    uint2 *ranges, uint32_t *acc /* 8 zeroed words */, uint32_t *info, cudaStream_t st,
+                    bool merge_sort = false /* the round-1 cub::BlockMergeSort kernel (GS_TUNE_STRATA_MERGE_SORT) */);
 // depth strata: per-view octiles of the depths of the binned Gaussians (weighted by their tile count), for the NEXT call
 size_t bin_strata_bytes(const DevCfg &c);          // strata table [V][BIN_SUB] floats + histogram scratch
 int bin_learn_strata(const DevCfg &c, const ushort4 *rects, const float4 *rec2, void *strata_buf, cudaStream_t st);

@@ -5,10 +5,11 @@ what=${@:-tests bench ab ncu}
 mkdir -p gpurun_out
 for w in $what; do
 case $w in
-tests) timeout 1500 python -m pytest tests -m gpu -x -q -s > gpurun_out/tests_$tag.log 2>&1; echo "tests rc=$?" ; tail -5 gpurun_out/tests_$tag.log ;;
+tests) timeout 1500 python -m pytest tests -m gpu -q -s > gpurun_out/tests_$tag.log 2>&1; echo "tests rc=$?" ; tail -5 gpurun_out/tests_$tag.log ;;
 newtests) timeout 1200 python -m pytest tests/test_gpu_config_sizes.py tests/test_gpu_parity.py -m gpu -q -s > gpurun_out/tests_$tag.log 2>&1; echo "tests rc=$?" ; tail -5 gpurun_out/tests_$tag.log ;;
 bench) timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; echo "bench rc=$?"; tail -c 600 gpurun_out/bench_$tag.json ;;
-ab) for t in 0 48 16 32; do GS_TUNING=$t timeout 300 python scripts/stage_times.py > gpurun_out/stages_${tag}_t$t.log 2>&1; echo "tuning $t:"; tail -2 gpurun_out/stages_${tag}_t$t.log; done ;;
-ncu) timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__thread_inst_executed_per_inst_executed.ratio,sm__issue_active.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"k_composite|k_preprocess|k_stratum|k_tile_sort" -s 30 -c 12 --csv --log-file gpurun_out/ncu_light_$tag.csv env GS_STEPS=5 python scripts/profile_step.py > gpurun_out/ncu_light_$tag.log 2>&1; echo "ncu rc=$?" ;;
+ab) for t in ${AB_TUNINGS:-0 64 32 16}; do GS_TUNING=$t timeout 300 python scripts/stage_times.py > gpurun_out/stages_${tag}_t$t.log 2>&1; echo "tuning $t:"; tail -2 gpurun_out/stages_${tag}_t$t.log; done ;;
+ncu) timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__thread_inst_executed_per_inst_executed.ratio,sm__issue_active.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"k_composite|k_preprocess|k_stratum|k_tile_sort" -s 25 -c 10 --csv --log-file gpurun_out/ncu_light_$tag.csv env GS_STEPS=8 python scripts/profile_step.py > gpurun_out/ncu_light_$tag.log 2>&1; echo "ncu rc=$?" ;;
+probe) timeout 120 scripts/probes/pcie_pull_probe > gpurun_out/pcie_probe_$tag.log 2>&1; cat gpurun_out/pcie_probe_$tag.log ;;
 esac
 done

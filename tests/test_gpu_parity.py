@@ -309,6 +309,29 @@ def test_binning_paths_agree_bit_for_bit():
     assert st2["speculative"] == 0 and torch.equal(color, color2)
 
 
+@pytest.mark.parametrize("levels", [8, 64, 4096])
+def test_stratum_sort_handles_depth_ties(levels):
+    """The hand-written warp-per-stratum sort forms its buckets on the depth bits.  Depths quantised to a few levels put
+    EXACT ties en masse into every stratum: 8 levels = one depth per stratum (buckets are then formed on the index), 64
+    levels = a handful of crowded buckets per stratum (ranked cooperatively), 4096 = ordinary small ties.  Lists must be
+    bit-identical to the exact path's and to the merge-sort kernel's."""
+    from pf3plat_b200._capi import GS_TUNE_NO_SPECULATION, GS_TUNE_STRATA_MERGE_SORT
+    dev = _dev()
+    sc = make_scene(60000, 2, 96, 96, seed=15)
+    z = sc.means[:, 2]
+    q = torch.exp(torch.round(torch.log(z) * (levels / 3.0)) / (levels / 3.0))     # log-spaced levels between 1.5 and 20
+    sc.means = sc.means * (q / z)[:, None]                                          # same pixel, quantised depth
+    exact, st0 = _render_with_tuning(sc, dev, GS_TUNE_NO_SPECULATION)
+    _render_with_tuning(sc, dev, 0)                                                 # strata trial
+    ours, st1 = _render_with_tuning(sc, dev, 0)
+    merge, st2 = _render_with_tuning(sc, dev, GS_TUNE_STRATA_MERGE_SORT)
+    assert st0["speculative"] == 0
+    if st1["speculative"] == 2:      # (a shape whose strata overflow falls back to whole-tile sorts: nothing to compare)
+        assert st2["speculative"] == 2
+    assert torch.equal(exact, ours) and torch.equal(exact, merge)
+    assert st0["num_rendered"] == st1["num_rendered"]
+
+
 def test_pixel_aligned_pf3plat_shaped_cloud():
     """2 x 128 x 128 pixel-aligned Gaussians (the structure PF3plat's encoder emits): neighbouring indices share
     tiles, lists are short, many splats are sub-pixel.  Forward and backward against the oracle."""
