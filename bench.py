@@ -195,6 +195,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback exists)"
     torch.cuda.set_device(local)
+    from pf3plat_b200.sharding import SharedCloudUploader, bind_to_gpu_numa_node
+    numa_cpus = bind_to_gpu_numa_node(local) if world > 1 else []   # before the pinned buffers are allocated (first touch)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -252,8 +254,35 @@ def main():
     stream = torch.cuda.current_stream(dev)
     ctx = rasterizer.current_context(dev)
 
-    def e2e():
+    def e2e_single():
         _capi.check(L.gs_render_host(ctx, ctypes.byref(hcfg), ctypes.byref(hin), ctypes.byref(hout), stream.cuda_stream))
+
+    # N > 1: the ranks of one box render different views of the SAME cloud.  Every rank uploads 1/N of the per-Gaussian
+    # arrays over its own PCIe link and one NCCL all-gather per array (NVLink) completes the cloud on every GPU
+    # (pf3plat_b200.sharding.SharedCloudUploader); cameras are per rank.  Then the device entry, then the results back.
+    uploader = None
+    if world > 1:
+        cloud_host = {"means3D": host["means3D"][0], "opacities": host["opacities"][0], "shs": host["shs"][0],
+                      "cov3D_precomp": host["cov3D_precomp"][0]}
+        uploader = SharedCloudUploader(cloud_host, dev)
+        cam_keys = ("viewmatrix", "projmatrix", "campos", "bg", "tanfov")
+        cam_dev = {k: torch.empty_like(host[k], device=dev) for k in cam_keys}
+        h2d = uploader.bytes_per_step + sum(host[k].numel() * 4 for k in cam_keys)
+
+    def e2e_shared():
+        with torch.no_grad():
+            for k in cam_keys:
+                cam_dev[k].copy_(host[k], non_blocking=True)
+            cl = uploader.upload()
+            bs_e = BatchSettings(image_height=HW, image_width=HW, viewmatrix=cam_dev["viewmatrix"], projmatrix=cam_dev["projmatrix"],
+                                 campos=cam_dev["campos"], bg=cam_dev["bg"], sh_degree=4, tanfov=cam_dev["tanfov"], tuning=args.tuning)
+            c_, r_ = rasterize_batch(bs_e, cl["means3D"][None], cl["opacities"][None], shs=cl["shs"][None],
+                                     cov3D_precomp=cl["cov3D_precomp"][None])
+            out_color.copy_(c_, non_blocking=True)
+            out_radii.copy_(r_, non_blocking=True)
+        stream.synchronize()
+
+    e2e = e2e_shared if world > 1 else e2e_single
 
     def barrier():
         if world > 1:
@@ -286,6 +315,9 @@ def main():
     vis = int((radii > 0).sum().item())
     e2e()
     assert torch.equal(out_color.to(dev), color), "host-buffer entry and device entry disagree"
+    if world > 1:
+        e2e_single()    # the single-rank entry agrees with the shared upload
+        assert torch.equal(out_color.to(dev), color)
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -528,7 +560,10 @@ def main():
             "views_per_sec": VIEWS * world * args.steps / (ms_fwd * 1e-3),
             "e2e": {"value": gauss_per_step * args.steps / (ms_e2e * 1e-3), "unit": "Gaussians/s",
                     "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "gs_render_host (C ABI, pinned host buffers)"},
+                    "api": "gs_render_host (C ABI, pinned host buffers)" if world == 1 else
+                           "SharedCloudUploader (1/N of the cloud per rank over PCIe + NCCL all-gather over NVLink) + "
+                           "rasterize_batch + D2H of the results; ranks bound to their GPU's NUMA node",
+                    "numa_cpus_rank0": len(numa_cpus)},
             "fwd_bwd": {"value": gauss_per_step * args.steps / (ms_fb * 1e-3), "unit": "Gaussians/s",
                         "ms_per_step": ms_fb / args.steps, "loss": "MSE to U(0,1) target"},
             "gpu_launches": (launches_fwd) * args.steps,

@@ -3,6 +3,8 @@ in the data path; the only exchange is a gather of per-
 the end.  One process per GPU, torch.distributed (NCCL on GPUs; gloo in the CPU tests)."""
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -49,3 +51,66 @@ def allreduce_scene_gradients(grads: list) -> None:
         n = g.numel()
         g.copy_(flat[off:off + n].view_as(g))
         off += n
+
+
+class SharedCloudUploader:
+    """Host -> device upload of a cloud EVERY rank needs (views of one scene sharded over the ranks of a box).
+
+    Naively each of the N ranks pushes the whole cloud over its own PCIe link (C2: 170 MB per rank, eight ranks sharing
+    two NUMA nodes' memory controllers: measured e2e efficiency 0.84 at N = 8 in round 1).  Here rank r copies only rows
+    [r P/N, (r+1) P/N) of every per-Gaussian array from (pinned) host memory into its slice of a device buffer and ONE
+    all-gather per array (NCCL over NVLink / NVSwitch on GPUs, in place: the send slice lives inside the receive buffer)
+    hands every rank the rest -- PCIe carries 1/N of the bytes, NVLink (900 GB/s per direction) the remainder.
+    Arrays are given as {name: host tensor [P, ...]}; P is padded up to a multiple of N internally."""
+
+    def __init__(self, host: dict, device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.host = host
+        self.P = next(iter(host.values())).shape[0]
+        self.chunk = -(-self.P // self.world)
+        self.dev = {k: torch.empty((self.chunk * self.world, *v.shape[1:]), dtype=v.dtype, device=device)
+                    for k, v in host.items()}
+        self.bytes_per_step = sum(min(self.chunk, max(0, self.P - self.rank * self.chunk)) * v[0].numel() * v.element_size()
+                                  for v in host.values())
+
+    def upload(self) -> dict:
+        """Enqueues the copies and the all-gathers on the current stream; returns {name: device tensor [P, ...]}."""
+        lo, hi = self.rank * self.chunk, min(self.P, (self.rank + 1) * self.chunk)
+        out = {}
+        for k, h in self.host.items():
+            d = self.dev[k]
+            if hi > lo:
+                d[lo:hi].copy_(h[lo:hi], non_blocking=True)
+            if self.world > 1:
+                flat = d.view(-1)
+                n = flat.numel() // self.world
+                mine = flat[self.rank * n:(self.rank + 1) * n]
+                if d.device.type != "cuda":
+                    mine = mine.clone()   # gloo (CPU tests) does not take an input that aliases the output
+                dist.all_gather_into_tensor(flat, mine, group=self.group)
+            out[k] = d[: self.P]
+        return out
+
+
+def bind_to_gpu_numa_node(device_index: int) -> list:
+    """Pins this process (and so the pinned host buffers it allocates afterwards: first touch) to the CPUs NVML reports as
+    local to the GPU -- on an 8-GPU box GPUs 0-3 and 4-7 hang off different sockets, and a rank that stages its uploads in
+    the other socket's memory pays the inter-socket hop on every copy.  Returns the CPU list in effect ([] = unchanged)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[device_index]) if vis and vis.split(",")[device_index].strip().isdigit() else device_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        local = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = local & set(os.sched_getaffinity(0))
+        if allowed and allowed != set(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, allowed)
+            return sorted(allowed)
+    except Exception:  # noqa: BLE001 -- no NVML, no permission, cpuset without local CPUs: leave the affinity alone
+        pass
+    return []

@@ -10,7 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from pf3plat_b200.cameras import make_view_batch
-from pf3plat_b200.sharding import allreduce_scene_gradients, gather_metric, shard_views
+from pf3plat_b200.sharding import SharedCloudUploader, allreduce_scene_gradients, gather_metric, shard_views
 from pf3plat_b200.synthetic import make_scene
 
 
@@ -31,7 +31,14 @@ def _worker(rank, world, port, out):
         # one scene's views split over the ranks: per-Gaussian gradient blocks are summed by ONE all-reduce
         g_means, g_sh = torch.full((100, 3), float(rank + 1)), torch.full((100, 25, 3), 10.0 * (rank + 1))
         allreduce_scene_gradients([g_means, None, g_sh])
-        out.put((rank, views, allp.tolist(), sc.extrinsics[:, :2, 3].tolist(), float(g_means[7, 1]), float(g_sh[3, 2, 1])))
+        # shared-cloud upload: each rank copies its 1/N of the rows, one all-gather per array fills in the rest (P = 101 is
+        # not a multiple of the world size: the padding rows stay outside the returned views)
+        g = torch.Generator().manual_seed(5)
+        host = {"means3D": torch.randn(101, 3, generator=g), "shs": torch.randn(101, 25, 3, generator=g)}
+        up = SharedCloudUploader(host, torch.device("cpu"))
+        got = up.upload()
+        same = all(torch.equal(got[k], host[k]) for k in host) and up.bytes_per_step < sum(v.numel() * 4 for v in host.values())
+        out.put((rank, views, allp.tolist(), sc.extrinsics[:, :2, 3].tolist(), float(g_means[7, 1]), float(g_sh[3, 2, 1]), same))
     finally:
         dist.destroy_process_group()
 
@@ -47,7 +54,8 @@ def test_view_sharding_and_psnr_gather_world2():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (r0, v0, g0, t0, m0, s0), (r1, v1, g1, t1, m1, s1) = res
+    (r0, v0, g0, t0, m0, s0, u0), (r1, v1, g1, t1, m1, s1, u1) = res
+    assert u0 and u1                                                # every rank ends up with the whole cloud
     assert m0 == m1 == 3.0 and s0 == s1 == 30.0                    # 1 + 2 and 10 + 20 on both ranks
     assert v0 == [0, 1, 2, 3] and v1 == [4, 5, 6, 7]               # contiguous, disjoint, complete
     assert g0 == g1 == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0]    # every rank sees every view's metric, in view order
