@@ -521,7 +521,16 @@ gso_handle *gso_forward(const gso_params *pp, const real *means3D, const real *s
                     n_pairs++;
                     if (power > 0) continue;
                     real alpha = rmin(RL(0.99), co[3] * R_EXP(power));
-                    if (frag_rel > 0 && R_FABS(alpha - inv255) <= frag_rel * inv255) frag = 1;
+                    /* Fragility band around alpha = 1/255: frag_rel, widened by the fp32 forward-error bound of the
+                     * quadratic form itself.  For a needle-shaped footprint evaluated far along its major axis the three
+                     * terms are hundreds of units each and cancel to a power of about -5: ANY fp32 evaluation (upstream's
+                     * order, this file's, a kernel's pre-scaled form) carries an absolute error of a few eps * sum|terms|
+                     * in the power, i.e. that much RELATIVE error in alpha -- beyond 1e-4 once sum|terms| > ~100. */
+                    if (frag_rel > 0) {
+                        real cond = RL(0.5) * (R_FABS(co[0]) * dx * dx + R_FABS(co[2]) * dy * dy) + R_FABS(co[1] * dx * dy);
+                        real band = frag_rel + RL(16.0) * RL(1.1920929e-7) * cond;
+                        if (R_FABS(alpha - inv255) <= band * inv255) frag = 1;
+                    }
                     if (alpha < inv255) continue;
                     real test_T = T * (RL(1.0) - alpha);
                     if (frag_rel > 0 && R_FABS(test_T - RL(0.0001)) <= frag_rel * RL(0.0001)) frag = 1;

@@ -52,6 +52,7 @@ k_tile_scan(int nvt, const uint32_t *__restrict__ counters, uint32_t *__restrict
     const int per = (nvt + SCAN_THREADS - 1) / SCAN_THREADS;  // tiles per thread
     const int b = threadIdx.x * per, e = min(nvt, b + per);
     uint32_t sum = 0, mx = 0, mxs = 0;
+    unsigned long long sum64 = 0;  // the offsets are 32-bit; the TOTAL is also taken in 64 bits so that a wrap is seen
     for (int t = b; t < e; t++) {
         uint32_t tn = 0;
 #pragma unroll
@@ -61,11 +62,18 @@ k_tile_scan(int nvt, const uint32_t *__restrict__ counters, uint32_t *__restrict
             mxs = max(mxs, cnt);
         }
         sum += tn;
+        sum64 += tn;
         mx = max(mx, tn);
     }
     uint32_t excl, total;
     BlockScan(tmp.scan).ExclusiveSum(sum, excl, total);
     __syncthreads();
+    {
+        using Reduce64 = cub::BlockReduce<unsigned long long, SCAN_THREADS>;
+        __shared__ typename Reduce64::TempStorage tmp64;
+        const unsigned long long total64 = Reduce64(tmp64).Sum(sum64);
+        if (threadIdx.x == 0 && total64 > 0xffffffffull) total = 0xffffffffu;  // saturate: the host rejects D > 2^31-1
+    }
     const uint32_t bmax = BlockReduce(tmp.reduce).Reduce(mx, cub::Max());
     __syncthreads();
     const uint32_t bmaxs = BlockReduce(tmp.reduce).Reduce(mxs, cub::Max());
@@ -196,10 +204,15 @@ k_spec_check(int nvt, uint32_t sub_cap, uint32_t tile_limit, const uint32_t *__r
             tn += cnt;
         }
         over |= tn > tile_limit ? 1u : 0u;
+        over |= sum + tn < sum ? 1u : 0u;  // a 32-bit wrap of the running total counts as an overflow (redone exactly)
         sum += tn;
         mx = max(mx, tn);
     }
     const uint32_t total = BlockReduce(tmp).Sum(sum);
+    __syncthreads();
+    using Reduce64 = cub::BlockReduce<unsigned long long, SCAN_THREADS>;
+    __shared__ typename Reduce64::TempStorage tmp64;
+    if (Reduce64(tmp64).Sum((unsigned long long)sum) > 0xffffffffull) over |= 1u;  // (thread 0 holds the block sum)
     __syncthreads();
     const uint32_t bmax = BlockReduce(tmp).Reduce(mx, cub::Max());
     __syncthreads();
@@ -485,7 +498,7 @@ k_stratum_sort(uint32_t nvt, uint32_t sub_cap, const uint32_t *__restrict__ curs
     const uint32_t base = vt * BIN_SUB * sub_cap;
     if (k == 0 && threadIdx.x == 0) {
         ranges[vt] = make_uint2(base, base + total);
-        atomicAdd(&acc[0], raw_total);
+        if (atomicAdd(&acc[0], raw_total) + raw_total < raw_total) atomicOr(&acc[3], 1u);  // 32-bit wrap: redo exactly
         atomicMax(&acc[1], raw_total);
         atomicMax(&acc[2], raw_max);
         if (raw_max > sub_cap) atomicOr(&acc[3], 1u);
@@ -517,20 +530,19 @@ k_stratum_sort(uint32_t nvt, uint32_t sub_cap, const uint32_t *__restrict__ curs
 // of binary searches, two CTA barriers each).  A stratum is small and its depths are spread over a narrow, roughly
 // uniform range, so one distribution pass nearly sorts it:
 //   1. warp min / max of the depth bits (REDUX);
-//   2. 32 depth buckets, bucket = floor((bits - min) * 32 / (range + 1)) -- monotone in the key, so sorted buckets
-//      concatenate to the sorted stratum.  Counting is ATOMIC-FREE: five ballots of the bucket number's bits give every
-//      lane L the mask of the round's keys that fall into bucket L (lane L keeps bucket L's count in a register);
+//   2. 64 depth buckets, bucket = floor((bits - min) * 64 / (range + 1)) -- monotone in the key, so sorted buckets
+//      concatenate to the sorted stratum.  Counting is ATOMIC-FREE: six ballots of the bucket number's bits give every
+//      lane L the masks of the round's keys that fall into buckets L and L + 32 (whose counts it keeps in registers);
 //   3. a warp scan turns counts into bucket offsets; a second sweep of the same ballots scatters the keys to their
 //      bucket in shared memory (position = bucket cursor + rank among the round's equal-bucket lanes);
-//   4. lane L insertion-sorts bucket L (~13 keys) on the full 64-bit (depth, index) key -- index ties included;
-//   5. the indices leave with coalesced stores.
-// A bucket of more than 32 keys (depth ties en masse: all depths equal -> buckets are formed on the index instead;
-// anything else that crowds) is ranked by the whole warp cooperatively and written straight to its final place: always
-// correct, only slower.  ~1 400 warp-instructions per stratum.
+//   4. every key is RANKED inside its bucket (~6 keys: one pass over the bucket's members per key, lanes = keys, so the
+//      work is balanced whatever the bucket sizes) on the full 64-bit (depth, index) key -- index ties included -- and
+//      its index is stored straight to its final position.
+// Depth ties en masse (all depths of the stratum equal) switch the buckets to the index bits; any other crowding only
+// lengthens step 4 (quadratic in the bucket, always correct).  First version (32 buckets, per-lane insertion sort):
+// 4 335 warp-instructions per stratum, 0.125 ms on C2 (merge sort: 5 760, 0.170 ms) -- the slowest lane's bucket set the pace.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int RS_WARPS = 4;          // strata per CTA (independent warps)
-constexpr uint32_t RS_BIG = 32;      // buckets longer than this are ranked cooperatively
-constexpr uint32_t RS_DONE = 0x80000000u;  // marks keys whose index has already been written (indices are < 2^31)
 
 __global__ void __launch_bounds__(RS_WARPS * 32)
 k_stratum_rank_sort(uint32_t nvt, uint32_t sub_cap, uint32_t cap_pad, const uint32_t *__restrict__ cursor,
@@ -552,7 +564,7 @@ k_stratum_rank_sort(uint32_t nvt, uint32_t sub_cap, uint32_t cap_pad, const uint
         const uint32_t raw_total = __reduce_add_sync(0xffffffffu, raw), raw_max = __reduce_max_sync(0xffffffffu, raw);
         if (lane == 0) {
             ranges[vt] = make_uint2(base, base + total);
-            atomicAdd(&acc[0], raw_total);
+            if (atomicAdd(&acc[0], raw_total) + raw_total < raw_total) atomicOr(&acc[3], 1u);  // 32-bit wrap: redo exactly
             atomicMax(&acc[1], raw_total);
             atomicMax(&acc[2], raw_max);
             if (raw_max > sub_cap) atomicOr(&acc[3], 1u);
@@ -591,85 +603,79 @@ k_stratum_rank_sort(uint32_t nvt, uint32_t sub_cap, uint32_t cap_pad, const uint
         lo = __reduce_min_sync(0xffffffffu, lo);
         hi = __reduce_max_sync(0xffffffffu, hi);
     }
-    const float scale = 32.0f / ((float)(hi - lo) + 1.0f);
+    const float scale = 64.0f / ((float)(hi - lo) + 1.0f);
     auto bucket_of = [&](uint64_t key) -> uint32_t {  // monotone in the key: int -> float -> int conversions all are
         const uint32_t x = by_index ? (uint32_t)key : (uint32_t)(key >> 32);
-        return min(31u, (uint32_t)(__uint2float_rz(x - lo) * scale));
+        return min(63u, (uint32_t)(__uint2float_rz(x - lo) * scale));
     };
-    // mask of the round's lanes whose key falls into bucket `lane`, from the ballots of the bucket number's five bits
+    // masks of the round's lanes whose key falls into bucket `lane` (lo) and `lane + 32` (hi), from the ballots of the
+    // bucket number's six bits
     const uint32_t x0 = (lane & 1u) ? 0u : ~0u, x1 = (lane & 2u) ? 0u : ~0u, x2 = (lane & 4u) ? 0u : ~0u,
                    x3 = (lane & 8u) ? 0u : ~0u, x4 = (lane & 16u) ? 0u : ~0u;
-    auto mine_mask = [&](uint32_t b, bool valid) -> uint32_t {
+    auto masks = [&](uint32_t b, bool valid, uint32_t &m_lo, uint32_t &m_hi) {
         uint32_t m = __ballot_sync(0xffffffffu, valid);
         m &= __ballot_sync(0xffffffffu, b & 1u) ^ x0;
         m &= __ballot_sync(0xffffffffu, b & 2u) ^ x1;
         m &= __ballot_sync(0xffffffffu, b & 4u) ^ x2;
         m &= __ballot_sync(0xffffffffu, b & 8u) ^ x3;
         m &= __ballot_sync(0xffffffffu, b & 16u) ^ x4;
-        return m;
+        const uint32_t top = __ballot_sync(0xffffffffu, b & 32u);
+        m_lo = m & ~top;
+        m_hi = m & top;
     };
     // 2. count
-    uint32_t count = 0;
+    uint32_t c_lo = 0, c_hi = 0;
     for (uint32_t r0 = 0; r0 < n; r0 += 32) {
         const uint32_t i = r0 + lane;
         const bool valid = i < n;
         const uint32_t b = valid ? bucket_of(src[i]) : 0u;
-        count += __popc(mine_mask(b, valid));
+        uint32_t m_lo, m_hi;
+        masks(b, valid, m_lo, m_hi);
+        c_lo += __popc(m_lo);
+        c_hi += __popc(m_hi);
     }
-    // 3. offsets, scatter
-    uint32_t incl = count;
+    // 3. offsets (buckets 0..31 first, then 32..63), scatter
+    uint32_t i_lo = c_lo, i_hi = c_hi;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-        if ((int)lane >= d) incl += t;
+        const uint32_t t_lo = __shfl_up_sync(0xffffffffu, i_lo, d), t_hi = __shfl_up_sync(0xffffffffu, i_hi, d);
+        if ((int)lane >= d) {
+            i_lo += t_lo;
+            i_hi += t_hi;
+        }
     }
-    const uint32_t start = incl - count;
-    uint32_t run = start;
+    const uint32_t s_lo = i_lo - c_lo, s_hi = __shfl_sync(0xffffffffu, i_lo, 31) + i_hi - c_hi;  // bucket starts
+    uint32_t run_lo = s_lo, run_hi = s_hi;
     const uint32_t lt = (1u << lane) - 1u;
     for (uint32_t r0 = 0; r0 < n; r0 += 32) {
         const uint32_t i = r0 + lane;
         const bool valid = i < n;
         const uint64_t key = valid ? src[i] : 0ull;
         const uint32_t b = valid ? bucket_of(key) : 0u;
-        const uint32_t m = mine_mask(b, valid);
-        const uint32_t same = __shfl_sync(0xffffffffu, m, b);     // the lanes whose key shares my bucket
-        const uint32_t at = __shfl_sync(0xffffffffu, run, b);     // that bucket's cursor
+        uint32_t m_lo, m_hi;
+        masks(b, valid, m_lo, m_hi);
+        const uint32_t owner = b & 31u;
+        const uint32_t same_lo = __shfl_sync(0xffffffffu, m_lo, owner), same_hi = __shfl_sync(0xffffffffu, m_hi, owner);
+        const uint32_t at_lo = __shfl_sync(0xffffffffu, run_lo, owner), at_hi = __shfl_sync(0xffffffffu, run_hi, owner);
+        const uint32_t same = (b & 32u) ? same_hi : same_lo, at = (b & 32u) ? at_hi : at_lo;
         if (valid) srt[at + __popc(same & lt)] = key;
-        run += __popc(m);
+        run_lo += __popc(m_lo);
+        run_hi += __popc(m_hi);
     }
     __syncwarp();
-    // 4. sort inside the buckets
-    uint32_t big = __ballot_sync(0xffffffffu, count > RS_BIG);
-    if (count <= RS_BIG) {
-        for (uint32_t a = start + 1; a < start + count; a++) {
-            const uint64_t key = srt[a];
-            uint32_t j = a;
-            while (j > start && srt[j - 1] > key) {
-                srt[j] = srt[j - 1];
-                j--;
-            }
-            srt[j] = key;
-        }
-    }
-    while (big) {  // a crowded bucket: the whole warp ranks its keys and stores their indices directly
-        const int owner = __ffs(big) - 1;
-        big &= big - 1u;
-        const uint32_t bs = __shfl_sync(0xffffffffu, start, owner), bn = __shfl_sync(0xffffffffu, count, owner);
-        for (uint32_t e0 = 0; e0 < bn; e0 += 32) {
-            const uint32_t e = e0 + lane;
-            const uint64_t key = e < bn ? srt[bs + e] : 0ull;
-            uint32_t rank = 0;
-            for (uint32_t q = 0; q < bn; q++) rank += srt[bs + q] < key ? 1u : 0u;  // keys are distinct: (depth, index)
-            if (e < bn) dst[bs + rank] = (uint32_t)key;
-        }
-        __syncwarp();
-        for (uint32_t e = lane; e < bn; e += 32) srt[bs + e] |= RS_DONE;
-    }
-    __syncwarp();
-    // 5. out
-    for (uint32_t i = lane; i < n; i += 32) {
-        const uint32_t id = (uint32_t)srt[i];
-        if (!(id & RS_DONE)) dst[i] = id;
+    // 4. rank every key inside its bucket; its index goes straight to its final position
+    for (uint32_t r0 = 0; r0 < n; r0 += 32) {
+        const uint32_t i = r0 + lane;
+        const bool valid = i < n;
+        const uint64_t key = valid ? src[i] : 0ull;
+        const uint32_t b = valid ? bucket_of(key) : 0u;
+        const uint32_t owner = b & 31u;
+        const uint32_t st_lo = __shfl_sync(0xffffffffu, s_lo, owner), st_hi = __shfl_sync(0xffffffffu, s_hi, owner);
+        const uint32_t n_lo = __shfl_sync(0xffffffffu, c_lo, owner), n_hi = __shfl_sync(0xffffffffu, c_hi, owner);
+        const uint32_t bs = (b & 32u) ? st_hi : st_lo, bn = valid ? ((b & 32u) ? n_hi : n_lo) : 0u;
+        uint32_t rank = 0;
+        for (uint32_t q = 0; q < bn; q++) rank += srt[bs + q] < key ? 1u : 0u;  // keys are distinct: (depth, index)
+        if (valid) dst[bs + rank] = (uint32_t)key;
     }
 }
 

@@ -326,6 +326,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     const DevCfg c = make_dev_cfg(cfg);
     const DevInputs di = make_dev_inputs(in);
     const size_t n = (size_t)c.V * c.P;
+    const bool pre_low = (cfg->tuning & GS_TUNE_PRE_OCC5) != 0;
     for (bool &v : ctx->ev_valid) v = false;
     ctx->stats.kernel_launches = 0;
 
@@ -379,10 +380,16 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     const bool speculate = ctx->spec.sub_cap > 0 && ctx->spec.V == c.V && ctx->spec.ntiles == c.ntiles && n > 0 &&
                            !(cfg->tuning & (GS_TUNE_FORCE_RADIX_BINNING | GS_TUNE_NO_SPECULATION));
     if (speculate) {
-        const bool strata = (ctx->spec.strata_state == STRATA_TRIAL || ctx->spec.strata_state == STRATA_ON) &&
-                            !(cfg->tuning & GS_TUNE_NO_STRATA) && ctx->strata.p != nullptr;
+        bool strata = (ctx->spec.strata_state == STRATA_TRIAL || ctx->spec.strata_state == STRATA_ON) &&
+                      !(cfg->tuning & GS_TUNE_NO_STRATA) && ctx->strata.p != nullptr;
         uint32_t sub_cap = ctx->spec.sub_cap;
-        if (strata && ctx->spec.strata_state == STRATA_TRIAL) sub_cap *= 2;  // capacities were learned unstratified
+        if (strata && ctx->spec.strata_state == STRATA_TRIAL) {
+            // capacities were learned unstratified: the trial runs on doubled ones -- if the kernels' 32-bit bucket
+            // offsets still hold them (learn_capacities checked the undoubled value only)
+            uint32_t trial = sub_cap * 2 > BIN_STRATUM_CAP ? BIN_STRATUM_CAP : sub_cap * 2;
+            if ((uint64_t)trial * BIN_SUB * nvt > 0xffffffffull) strata = false;
+            else sub_cap = trial;
+        }
         if (strata && sub_cap > BIN_STRATUM_CAP) sub_cap = BIN_STRATUM_CAP;
         const float *strata_tab = strata ? static_cast<const float *>(ctx->strata.p) : nullptr;
         const size_t slots = nvt * BIN_SUB;
@@ -407,10 +414,10 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
                     e = cudaStreamWaitEvent(st, ctx->feed_ev[k], 0);
                     if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "cudaStreamWaitEvent(feed)", __FILE__, __LINE__));
                     rc = launch_preprocess(c, di, s->rec0, s->rec1, s->rec2, s->meta, out->radii, rects, emit, st,
-                                           ctx->feed_begin[k], ctx->feed_begin[k + 1]);
+                                           ctx->feed_begin[k], ctx->feed_begin[k + 1], pre_low);
                 }
             } else {
-                rc = launch_preprocess(c, di, s->rec0, s->rec1, s->rec2, s->meta, out->radii, rects, emit, st);
+                rc = launch_preprocess(c, di, s->rec0, s->rec1, s->rec2, s->meta, out->radii, rects, emit, st, 0, -1, pre_low);
             }
             if (rc != GS_OK) return fail(rc);
         }
@@ -524,7 +531,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
             e = cudaStreamWaitEvent(st, ctx->feed_ev[k], 0);
             if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "cudaStreamWaitEvent(feed)", __FILE__, __LINE__));
         }
-        rc = launch_preprocess(c, di, s->rec0, s->rec1, s->rec2, s->meta, out->radii, rects, emit, st);
+        rc = launch_preprocess(c, di, s->rec0, s->rec1, s->rec2, s->meta, out->radii, rects, emit, st, 0, -1, pre_low);
         if (rc != GS_OK) return fail(rc);
         ctx->stats.kernel_launches += (c.P > 0);
     }
@@ -630,7 +637,7 @@ extern "C" int gs_backward(GsContext *ctx, const GsConfig *cfg, const GsInputs *
     {
         StageTimer t(ctx, GS_STAGE_COMPOSITE_BWD, st);
         GS_CUDA_OK(cudaMemsetAsync(acc, 0, n * GS_ACC_STRIDE * 4, st));
-        rc = launch_composite_bwd(c, *saved, gout->dL_dcolor, gout->dL_ddepth, acc, st, (cfg->tuning & GS_TUNE_BWD_V1) ? 1 : 0);
+        rc = launch_composite_bwd(c, *saved, gout->dL_dcolor, gout->dL_ddepth, acc, st, (cfg->tuning & GS_TUNE_BWD_V1) ? 1 : ((cfg->tuning & GS_TUNE_BWD_OCC4) ? 2 : 0));
         if (rc != GS_OK) return rc;
     }
     {

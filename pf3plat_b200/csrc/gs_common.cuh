@@ -70,7 +70,7 @@ struct PreEmit {
 };
 int launch_preprocess(const DevCfg &c, const DevInputs &in, float4 *rec0, float4 *rec1, float4 *rec2, uint8_t *meta,
                       int32_t *radii, ushort4 *rects, const PreEmit &emit, cudaStream_t st, int g_begin = 0,
-                      int g_end = -1 /* = P */);
+                      int g_end = -1 /* = P */, bool low_occupancy = false /* 96 registers, 5 CTAs/SM (GS_TUNE_PRE_OCC5) */);
 int launch_mark_visible(const DevCfg &c, const float *means3D, uint8_t *present, cudaStream_t st);
 
 // binning (gs_binning.cu)

@@ -444,12 +444,27 @@ k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
             uint32_t mask = __ballot_sync(0xffffffffu, hit);
             // this pixel takes the entries at list positions < last, i.e. bits b < last - (lo + chunk) of this round
             const int rel_last = (int)min(32u, last - min(last, lo + (uint32_t)chunk));
+            // the records of the NEXT survivor are fetched while the current one is worked on (the walk is one long
+            // dependent chain per survivor: shared-memory load -> power -> ex2 -> tests -> rcp -> ...)
+            int b_next = mask ? 31 - __clz(mask) : 0;  // deepest first
+            float4 q0n = make_float4(0.f, 0.f, 0.f, 0.f), q1n = q0n;
+            if (mask) {
+                const uint32_t an = rec_addr + ((uint32_t)chunk + b_next) * 48u;
+                q0n = lds128(an);
+                q1n = lds128(an + 16u);
+            }
             while (mask) {
-                const int b = 31 - __clz(mask);  // deepest first
+                const int b = b_next;
                 mask &= ~(1u << b);
                 const uint32_t jj = (uint32_t)chunk + b;
                 const uint32_t a = rec_addr + jj * 48u;
-                const float4 q0 = lds128(a), q1 = lds128(a + 16u);
+                const float4 q0 = q0n, q1 = q1n;
+                if (mask) {
+                    b_next = 31 - __clz(mask);
+                    const uint32_t an = rec_addr + ((uint32_t)chunk + b_next) * 48u;
+                    q0n = lds128(an);
+                    q1n = lds128(an + 16u);
+                }
                 const float dx = q0.x - pxf, dy = q0.y - pyf;
                 const float p2 = gs_power2(q0.z, q0.w, q1.x, dx, dy);
                 const float G = gs_ex2(p2);
@@ -490,16 +505,21 @@ int launch_composite_bwd(const DevCfg &c, const GsSaved &s, const float *dL_dcol
     if (c.V == 0 || c.ntiles == 0) return GS_OK;
     dim3 grid(c.ntiles, c.V);
     if (variant != 1) {
-        // v2 (default): 68 KB of shared memory, 3 CTAs/SM
-        constexpr int BATCH = CB_BATCH_MAX, MINB = 3;
-        const size_t smem = sizeof(Cb2Smem<BATCH>);
-        auto launch = [&](auto kern) -> int {
+        // v2.  variant 0: batch of 256 entries, 68 KB of shared memory, 80 registers, 3 CTAs/SM;
+        //      variant 2: batch of 128, 55 KB, registers bounded to 64 -> 4 CTAs/SM (the kernel is latency-bound at
+        //      24 resident warps: ncu issue-active 57 %)
+        auto launch = [&](auto kern, size_t smem) -> int {
             GS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<grid, CB_THREADS, smem, st>>>(c, s.rec0, s.rec1, s.rec2, s.point_list, s.ranges, s.final_T, s.n_contrib,
                                                  dL_dcolor, dL_ddepth, grad_acc);
             return GS_OK;
         };
-        const int rc = (c.flags & GS_FLAG_DEPTH) ? launch(k_composite_bwd<true, BATCH, MINB>) : launch(k_composite_bwd<false, BATCH, MINB>);
+        const bool dep = (c.flags & GS_FLAG_DEPTH) != 0;
+        int rc;
+        if (variant == 2)
+            rc = dep ? launch(k_composite_bwd<true, 128, 4>, sizeof(Cb2Smem<128>)) : launch(k_composite_bwd<false, 128, 4>, sizeof(Cb2Smem<128>));
+        else
+            rc = dep ? launch(k_composite_bwd<true, 256, 3>, sizeof(Cb2Smem<256>)) : launch(k_composite_bwd<false, 256, 3>, sizeof(Cb2Smem<256>));
         if (rc != GS_OK) return rc;
         GS_CUDA_OK(cudaGetLastError());
         return GS_OK;

@@ -126,8 +126,10 @@ __device__ __forceinline__ void project_splat(const DevCfg &c, const ViewCam &ca
     out.r2 = make_float4(rgb.z, pv.z, reach2, 0.0f);
 }
 
-template <bool HAS_SH>
-__global__ void __launch_bounds__(PRE_THREADS)
+// MINB: resident CTAs per SM the register allocation is bounded for.  Unbounded the kernel takes 96 registers (5 CTAs/SM,
+// 28 % occupancy; ncu: issue slots 50 % busy, latency-bound); 8 bounds it to 64 registers (116 bytes of spills).
+template <bool HAS_SH, int MINB>
+__global__ void __launch_bounds__(PRE_THREADS, MINB)
 k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, float4 *__restrict__ rec1,
              float4 *__restrict__ rec2, uint8_t *__restrict__ meta, int32_t *__restrict__ radii,
              ushort4 *__restrict__ rects, const PreEmit emit, const int g_begin, const int g_end) {
@@ -143,21 +145,36 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
     const bool active = tid < n;
     const size_t sg = (size_t)scene * c.P + i;  // scene-level index
 
-    // ---- stage this CTA's SH block (n * M * 3 contiguous floats) with one bulk TMA copy ----
+    // ---- stage this CTA's SH block ----
+    // Only the bands the evaluator can touch are staged: MS = min(M, 16) coefficients per Gaussian (PF3plat hands over
+    // M = 25 of which 16..24 are never read): 192 instead of 300 bytes of shared memory per thread, which is what lets
+    // eight CTAs share an SM.  M <= 16: the block is contiguous and arrives by ONE 1-D bulk TMA copy (cp.async.bulk,
+    // SASS UBLKCP) completing on an mbarrier.  M > 16: the wanted 192 bytes of every 12*M-byte row are copied with
+    // coalesced loads (rows are not 16-byte aligned -- 300 = 18 * 16 + 12 -- so neither a bulk copy per row nor a 2-D
+    // tensor map is possible).
+    const int MS = c.M < 16 ? c.M : 16;
     bool bulk = false;
     if (HAS_SH) {
         const float *src = in.shs + ((size_t)scene * c.P + g0) * c.M * 3;
-        const uint32_t bytes = (uint32_t)n * c.M * 12u;
-        bulk = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && ((bytes & 15u) == 0);
-        if (bulk) {
-            if (tid == 0) {
-                mbar_init(&sm->bar, 1);
-                mbar_fence_init();
-                mbar_expect_tx(&sm->bar, bytes);
-                tma_load_1d(sh_s, src, bytes, &sm->bar);
+        if (c.M == MS) {
+            const uint32_t bytes = (uint32_t)n * c.M * 12u;
+            bulk = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && ((bytes & 15u) == 0);
+            if (bulk) {
+                if (tid == 0) {
+                    mbar_init(&sm->bar, 1);
+                    mbar_fence_init();
+                    mbar_expect_tx(&sm->bar, bytes);
+                    tma_load_1d(sh_s, src, bytes, &sm->bar);
+                }
+            } else {  // unaligned slice or ragged tail: plain coalesced copy
+                for (uint32_t k = tid; k < (uint32_t)n * c.M * 3u; k += PRE_THREADS) sh_s[k] = src[k];
             }
-        } else {  // unaligned slice or ragged tail: plain coalesced copy
-            for (uint32_t k = tid; k < (uint32_t)n * c.M * 3u; k += PRE_THREADS) sh_s[k] = src[k];
+        } else {
+            const uint32_t row_f = (uint32_t)c.M * 3u;
+            for (uint32_t e = tid; e < (uint32_t)n * 48u; e += PRE_THREADS) {
+                const uint32_t row = e / 48u, col = e - row * 48u;
+                sh_s[e] = __ldg(src + (size_t)row * row_f + col);
+            }
         }
     }
     // ---- scene-level inputs (issued while the bulk copy is in flight) ----
@@ -213,7 +230,7 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
             const int v = scene * c.VPS + v0 + vi;
             const size_t o = (size_t)v * c.P + i;
             Splat sp;
-            project_splat<HAS_SH>(c, sm->cams[vi], mean, c6, opac, sh_s + (size_t)tid * c.M * 3,
+            project_splat<HAS_SH>(c, sm->cams[vi], mean, c6, opac, sh_s + (size_t)tid * MS * 3,
                                   HAS_SH ? nullptr : in.colors_precomp + o * 3, sp);
             if (sp.radius > 0) {
                 rec0[o] = sp.r0;
@@ -295,18 +312,21 @@ __global__ void k_mark_visible(const DevCfg c, const float *__restrict__ means3D
 }  // namespace
 
 int launch_preprocess(const DevCfg &c, const DevInputs &in, float4 *rec0, float4 *rec1, float4 *rec2, uint8_t *meta,
-                      int32_t *radii, ushort4 *rects, const PreEmit &emit, cudaStream_t st, int g_begin, int g_end) {
+                      int32_t *radii, ushort4 *rects, const PreEmit &emit, cudaStream_t st, int g_begin, int g_end,
+                      bool low_occupancy) {
     if (g_end < 0) g_end = c.P;
     if (g_end <= g_begin) return GS_OK;
     dim3 grid((g_end - g_begin + PRE_THREADS - 1) / PRE_THREADS, c.S);
-    if (in.shs) {
-        size_t smem = PRE_SMEM_HDR + (size_t)PRE_THREADS * c.M * 12;
-        GS_CUDA_OK(cudaFuncSetAttribute(k_preprocess<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_preprocess<true><<<grid, PRE_THREADS, smem, st>>>(c, in, rec0, rec1, rec2, meta, radii, rects, emit, g_begin, g_end);
-    } else {
-        k_preprocess<false><<<grid, PRE_THREADS, PRE_SMEM_HDR, st>>>(c, in, rec0, rec1, rec2, meta, radii, rects, emit, g_begin,
-                                                                     g_end);
-    }
+    const size_t smem = PRE_SMEM_HDR + (in.shs ? (size_t)PRE_THREADS * (c.M < 16 ? c.M : 16) * 12 : 0);
+    auto launch = [&](auto kern) -> int {
+        GS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, PRE_THREADS, smem, st>>>(c, in, rec0, rec1, rec2, meta, radii, rects, emit, g_begin, g_end);
+        return GS_OK;
+    };
+    int rc;
+    if (in.shs) rc = low_occupancy ? launch(k_preprocess<true, 5>) : launch(k_preprocess<true, 8>);
+    else rc = low_occupancy ? launch(k_preprocess<false, 5>) : launch(k_preprocess<false, 8>);
+    if (rc != GS_OK) return rc;
     GS_CUDA_OK(cudaGetLastError());
     return GS_OK;
 }

@@ -88,6 +88,12 @@ def image_report(gpu_color, orc) -> dict:
 def check_image_strict(gpu_color, orc, max_fragile_frac: float, label: str = "") -> dict:
     rep = image_report(gpu_color, orc)
     print(f"[parity] {label} {rep}")
+    if rep["max_err_nonfragile"] > RGB_TOL:   # say where, so that the pixel can be examined on the CPU
+        g = gpu_color.detach().cpu().numpy() if torch.is_tensor(gpu_color) else np.asarray(gpu_color)
+        err = np.abs(g.astype(np.float64) - orc.color.astype(np.float64)).max(axis=0) * ~orc.px_fragile
+        y, x = np.unravel_index(np.argmax(err), err.shape)
+        print(f"[parity] {label} worst non-fragile pixel (y={y}, x={x}): ours {g[:, y, x]}, oracle {orc.color[:, y, x]}, "
+              f"final_T {orc.final_T[y, x]}, n_contrib {orc.n_contrib[y, x]}")
     assert rep["fragile_frac"] <= max_fragile_frac, rep
     assert rep["max_err_nonfragile"] <= RGB_TOL, rep
     assert rep["max_err_fragile"] <= FRAGILE_RGB_TOL, rep
