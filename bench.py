@@ -355,7 +355,16 @@ def main():
         fwd_moving(); fwd_moving(); fwd_moving()                    # exact -> trial -> steady state
         state.update(overflows=0, calls=0)
         ms_mov = timed(fwd_moving, args.steps, args.warmup)
-        moving = {"ms_per_step": ms_mov / args.steps, "value": gauss_per_step * args.steps / (ms_mov * 1e-3),
+        rasterizer.set_profiling(True, dev)
+        acc_m = {}
+        for _ in range(5):
+            fwd_moving()
+            for k_, v_ in rasterizer.stage_ms(dev).items():
+                acc_m.setdefault(k_, []).append(v_)
+        rasterizer.set_profiling(False, dev)
+        moving = {"stage_ms": {k_: statistics.mean(v_) for k_, v_ in acc_m.items()},
+                  "tile_instances_last": rasterizer.last_stats(dev)["num_rendered"],
+                  "ms_per_step": ms_mov / args.steps, "value": gauss_per_step * args.steps / (ms_mov * 1e-3),
                   "unit": "Gaussians/s", "overflow_rate": state["overflows"] / max(1, state["calls"]),
                   "calls": state["calls"], "variants": nvar,
                   "perturbation": "means jittered by N(0, 1 px) in x/y, 5 % of the Gaussians moved to another Gaussian's position, every step"}

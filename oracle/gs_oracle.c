@@ -525,10 +525,17 @@ gso_handle *gso_forward(const gso_params *pp, const real *means3D, const real *s
                      * quadratic form itself.  For a needle-shaped footprint evaluated far along its major axis the three
                      * terms are hundreds of units each and cancel to a power of about -5: ANY fp32 evaluation (upstream's
                      * order, this file's, a kernel's pre-scaled form) carries an absolute error of a few eps * sum|terms|
-                     * in the power, i.e. that much RELATIVE error in alpha -- beyond 1e-4 once sum|terms| > ~100. */
+                     * in the power, i.e. that much RELATIVE error in alpha -- beyond 1e-4 once sum|terms| > ~100.
+                     * Second fp32 limit: the projected centre itself.  ndc2Pix evaluates ((v + 1) * S - 1) / 2 with
+                     * (v + 1) * S up to 2S, so a pixel coordinate is only defined to about eps * S (6e-5 px at S = 512) --
+                     * contracting the expression into an fma or not already moves it by that much -- and a sharp
+                     * footprint (conic up to 1 / dilation = 3.3) turns that into |grad power| * 6e-5 ~ 2e-4 of alpha.
+                     * (Found on C4: one of 262 144 pixels, a Gaussian at alpha = 0.99985 / 255, worth 1e-3 of colour.) */
                     if (frag_rel > 0) {
                         real cond = RL(0.5) * (R_FABS(co[0]) * dx * dx + R_FABS(co[2]) * dy * dy) + R_FABS(co[1] * dx * dy);
-                        real band = frag_rel + RL(16.0) * RL(1.1920929e-7) * cond;
+                        real pos_err = RL(1.1920929e-7) * (real)(W > H ? W : H);
+                        real slope = R_FABS(co[0] * dx + co[1] * dy) + R_FABS(co[2] * dy + co[1] * dx);
+                        real band = frag_rel + RL(16.0) * RL(1.1920929e-7) * cond + pos_err * slope;
                         if (R_FABS(alpha - inv255) <= band * inv255) frag = 1;
                     }
                     if (alpha < inv255) continue;

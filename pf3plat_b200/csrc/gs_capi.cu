@@ -386,7 +386,13 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
         if (strata && ctx->spec.strata_state == STRATA_TRIAL) {
             // capacities were learned unstratified: the trial runs on doubled ones -- if the kernels' 32-bit bucket
             // offsets still hold them (learn_capacities checked the undoubled value only)
-            uint32_t trial = sub_cap * 2 > BIN_STRATUM_CAP ? BIN_STRATUM_CAP : sub_cap * 2;
+            // A cloud whose tiles each see a narrow depth range (PF3plat's pixel-aligned Gaussians on a smooth surface)
+            // puts a tile's whole list into one or two of the per-view strata: the trial must be able to hold a whole
+            // list per stratum, memory permitting (the capacities learned from it are what later calls allocate).
+            uint32_t trial = sub_cap * 2;
+            const uint32_t whole = ctx->spec.tile_limit < BIN_STRATUM_CAP ? ctx->spec.tile_limit : BIN_STRATUM_CAP;
+            if (whole > trial && (uint64_t)whole * BIN_SUB * nvt * 12ull <= ((uint64_t)1 << 30)) trial = whole;
+            if (trial > BIN_STRATUM_CAP) trial = BIN_STRATUM_CAP;
             if ((uint64_t)trial * BIN_SUB * nvt > 0xffffffffull) strata = false;
             else sub_cap = trial;
         }
@@ -485,11 +491,19 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
             if (strata) {
                 // capacities for the next call from the stratified counts just measured; a stratum beyond the small
                 // sort's capacity sends this shape back to whole-tile sorts (via one exact-path call)
-                const uint32_t next = ctx->h_word[2] + ctx->h_word[2] * 3 / 10 + 16;
+                uint32_t next = ctx->h_word[2] + ctx->h_word[2] * 3 / 10 + 16;
+                if (next > BIN_STRATUM_CAP && ctx->h_word[2] + ctx->h_word[2] / 10 <= BIN_STRATUM_CAP) next = BIN_STRATUM_CAP;  // 10 % headroom still fits
                 if (next > BIN_STRATUM_CAP) {
                     ctx->spec.strata_state = STRATA_OFF;
                     ctx->spec.sub_cap = 0;
                 } else {
+                    if (ctx->spec.strata_state == STRATA_TRIAL && ctx->sort.bytes > 2 * (slots * (size_t)next * 8) + ((size_t)8 << 20)) {
+                        // the trial's generous buckets are not needed again: give the block back (stream-ordered)
+                        if (ctx->sort.pooled) cudaFreeAsync(ctx->sort.p, st);
+                        else cudaFree(ctx->sort.p);
+                        ctx->sort.p = nullptr;
+                        ctx->sort.bytes = 0;
+                    }
                     ctx->spec.strata_state = STRATA_ON;
                     ctx->spec.sub_cap = next;
                 }
@@ -642,7 +656,7 @@ extern "C" int gs_backward(GsContext *ctx, const GsConfig *cfg, const GsInputs *
     }
     {
         StageTimer t(ctx, GS_STAGE_PREPROCESS_BWD, st);
-        rc = launch_preprocess_bwd(c, di, *saved, acc, *gin, st);
+        rc = launch_preprocess_bwd(c, di, *saved, acc, *gin, st, (cfg->tuning & GS_TUNE_PBWD_V1) ? 1 : 0);
         if (rc != GS_OK) return rc;
     }
     ctx->stats.kernel_launches += 2;  // k_composite_bwd, k_preprocess_bwd

@@ -109,7 +109,7 @@ int launch_composite_bwd(const DevCfg &c, const GsSaved &s, const float *dL_dcol
                          float *grad_acc /* [V*P*GS_ACC_STRIDE], zeroed */, cudaStream_t st,
                          int variant = 0 /* 1: the round-1 kernel (GS_TUNE_BWD_V1) */);
 int launch_preprocess_bwd(const DevCfg &c, const DevInputs &in, const GsSaved &s, const float *grad_acc,
-                          const GsInGrads &g, cudaStream_t st);
+                          const GsInGrads &g, cudaStream_t st, int variant = 0 /* 1: the round-1 kernel (GS_TUNE_PBWD_V1) */);
 
 // per (view,Gaussian) accumulator written by the composite backward:
 //   0-2 dL/drgb, 3-4 dL/dmean2D (NDC-scaled), 5-7 dL/dconic (a, b stored once, c), 8 dL/dopacity, 9 dL/dz
@@ -353,6 +353,10 @@ __device__ __forceinline__ float2 lds64(uint32_t addr) {
 // while they work on the current one
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+// 4-byte cp.async: gathers of rows that are only 4-byte aligned (the 12*M-byte SH rows)
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>

@@ -444,27 +444,14 @@ k_composite_bwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
             uint32_t mask = __ballot_sync(0xffffffffu, hit);
             // this pixel takes the entries at list positions < last, i.e. bits b < last - (lo + chunk) of this round
             const int rel_last = (int)min(32u, last - min(last, lo + (uint32_t)chunk));
-            // the records of the NEXT survivor are fetched while the current one is worked on (the walk is one long
-            // dependent chain per survivor: shared-memory load -> power -> ex2 -> tests -> rcp -> ...)
-            int b_next = mask ? 31 - __clz(mask) : 0;  // deepest first
-            float4 q0n = make_float4(0.f, 0.f, 0.f, 0.f), q1n = q0n;
-            if (mask) {
-                const uint32_t an = rec_addr + ((uint32_t)chunk + b_next) * 48u;
-                q0n = lds128(an);
-                q1n = lds128(an + 16u);
-            }
+            // (Prefetching the next survivor's records while the current one is worked on was tried: +3 % on C2 -- the
+            // extra live registers cost more than the shared-memory latency they hide.)
             while (mask) {
-                const int b = b_next;
+                const int b = 31 - __clz(mask);  // deepest first
                 mask &= ~(1u << b);
                 const uint32_t jj = (uint32_t)chunk + b;
                 const uint32_t a = rec_addr + jj * 48u;
-                const float4 q0 = q0n, q1 = q1n;
-                if (mask) {
-                    b_next = 31 - __clz(mask);
-                    const uint32_t an = rec_addr + ((uint32_t)chunk + b_next) * 48u;
-                    q0n = lds128(an);
-                    q1n = lds128(an + 16u);
-                }
+                const float4 q0 = lds128(a), q1 = lds128(a + 16u);
                 const float dx = q0.x - pxf, dy = q0.y - pyf;
                 const float p2 = gs_power2(q0.z, q0.w, q1.x, dx, dy);
                 const float G = gs_ex2(p2);

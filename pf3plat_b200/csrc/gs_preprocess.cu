@@ -170,11 +170,14 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
                 for (uint32_t k = tid; k < (uint32_t)n * c.M * 3u; k += PRE_THREADS) sh_s[k] = src[k];
             }
         } else {
+            // asynchronous 4-byte copies (cp.async, SASS LDGSTS): all 48 per thread are in flight together while the
+            // scalar inputs load -- a plain load/store loop here cost 0.25 ms on C2 (serialised latencies)
             const uint32_t row_f = (uint32_t)c.M * 3u;
             for (uint32_t e = tid; e < (uint32_t)n * 48u; e += PRE_THREADS) {
                 const uint32_t row = e / 48u, col = e - row * 48u;
-                sh_s[e] = __ldg(src + (size_t)row * row_f + col);
+                cp_async4(sh_s + e, src + (size_t)row * row_f + col);
             }
+            cp_async_commit();
         }
     }
     // ---- scene-level inputs (issued while the bulk copy is in flight) ----
@@ -195,7 +198,8 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
         }
     }
     if (HAS_SH) {
-        __syncthreads();  // barrier init (bulk) or the copy loop (fallback) visible to everyone
+        cp_async_wait<0>();  // this thread's share of the strided copy (no-op on the other paths)
+        __syncthreads();     // barrier init (bulk) or the copies (fallbacks) visible to everyone
         if (bulk) mbar_wait(&sm->bar, 0);
     }
 
