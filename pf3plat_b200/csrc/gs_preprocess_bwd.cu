@@ -359,6 +359,8 @@ k_preprocess_bwd(const DevCfg c, const DevInputs in, const uint8_t *__restrict__
     const bool active = tid < n;
     const size_t sg = (size_t)scene * c.P + i;
     const int MS = c.M < PB_SH_EVAL ? c.M : PB_SH_EVAL;   // coefficients staged per Gaussian
+    const int RS = c.M == MS ? MS * 3 : MS * 3 + 1;       // floats per staged row: compacted rows get an odd stride (no
+                                                          // 16-way bank conflicts between the threads of a warp)
     const uint32_t stage_floats = (uint32_t)n * MS * 3u;
 
     bool bulk = false;
@@ -378,7 +380,7 @@ k_preprocess_bwd(const DevCfg c, const DevInputs in, const uint8_t *__restrict__
             const uint32_t row_f = (uint32_t)c.M * 3u, take = (uint32_t)MS * 3u;
             for (uint32_t e = tid; e < stage_floats; e += PB_THREADS) {   // asynchronous 4-byte gathers (LDGSTS)
                 const uint32_t row = e / take, col = e - row * take;
-                cp_async4(sh_s + e, src + (size_t)row * row_f + col);
+                cp_async4(sh_s + row * RS + col, src + (size_t)row * row_f + col);
             }
             cp_async_commit();
         }
@@ -553,7 +555,7 @@ k_preprocess_bwd(const DevCfg c, const DevInputs in, const uint8_t *__restrict__
 
     // ================= phases S_0..S_2: colour -> SH coefficients and mean (view direction), one channel at a time ====
     if (HAS_SH) {
-        float *row = sh_s + (size_t)tid * MS * 3;
+        float *row = sh_s + (size_t)tid * RS;
 #pragma unroll 1
         for (int ch = 0; ch < 3; ch++) {
             float gsh[PB_SH_EVAL];
@@ -612,7 +614,7 @@ k_preprocess_bwd(const DevCfg c, const DevInputs in, const uint8_t *__restrict__
             const uint32_t row_f = (uint32_t)c.M * 3u, take = (uint32_t)MS * 3u, total = (uint32_t)n * row_f;
             for (uint32_t e = tid; e < total; e += PB_THREADS) {
                 const uint32_t r = e / row_f, col = e - r * row_f;
-                dst[e] = col < take ? sh_s[r * take + col] : 0.f;
+                dst[e] = col < take ? sh_s[r * RS + col] : 0.f;
             }
         }
     }
@@ -633,7 +635,7 @@ int launch_preprocess_bwd(const DevCfg &c, const DevInputs &in, const GsSaved &s
             k_preprocess_bwd_v1<false, PB_MIN_CTAS><<<grid, PB_THREADS, PB_SMEM_HDR, st>>>(c, in, s.meta, grad_acc, g);
         }
     } else if (in.shs) {
-        size_t smem = PB_SMEM_HDR + (size_t)PB_THREADS * (c.M < PB_SH_EVAL ? c.M : PB_SH_EVAL) * 12;
+        size_t smem = PB_SMEM_HDR + (size_t)PB_THREADS * (c.M <= PB_SH_EVAL ? c.M * 3 : PB_SH_EVAL * 3 + 1) * 4;
         GS_CUDA_OK(cudaFuncSetAttribute(k_preprocess_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_preprocess_bwd<true><<<grid, PB_THREADS, smem, st>>>(c, in, s.meta, grad_acc, g);
     } else {
