@@ -65,8 +65,8 @@ enum {
     GS_TUNE_FWD_V1 = 32u,             /* forward compositor: the round-1 kernel (one CTA per tile, all-thread cp.async staging, CTA barriers) instead of the persistent warp-specialised kernel (A/B) */
     GS_TUNE_STRATA_MERGE_SORT = 64u,  /* stratified binning: sort the strata with the round-1 cub::BlockMergeSort kernel instead of the hand-written warp-per-stratum distribution sort (A/B) */
     GS_TUNE_BWD_OCC4 = 128u,          /* backward compositor: batches of 128 entries and 64 registers (4 CTAs/SM) instead of 256 / 80 (3 CTAs/SM) (A/B) */
-    GS_TUNE_PRE_OCC5 = 4096u,         /* preprocess: unbounded registers (96, 5 CTAs/SM) instead of 64 (8 CTAs/SM) (A/B) */
-    GS_TUNE_PBWD_V1 = 8192u,          /* preprocess backward: the round-1 single-pass kernel (128 registers) instead of the two-phase kernel (A/B) */
+    GS_TUNE_PRE_OCC6 = 4096u,         /* preprocess: registers bounded to 80 (6 CTAs/SM) instead of unbounded (96, 5 CTAs/SM) (A/B) */
+    GS_TUNE_PBWD_2PHASE = 8192u,      /* preprocess backward: the two-phase kernel (geometry, then one pass per colour channel: 80 registers) instead of the single-pass one (128 registers) (A/B: slower) */
     GS_TUNE_FEED_PIECES_SHIFT = 8     /* gs_render_host: bits 8..11 = pieces the SH block is copied in (0 default, 1 = one plain copy) */
 };
 

@@ -336,7 +336,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     const DevCfg c = make_dev_cfg(cfg);
     const DevInputs di = make_dev_inputs(in);
     const size_t n = (size_t)c.V * c.P;
-    const bool pre_low = (cfg->tuning & GS_TUNE_PRE_OCC5) != 0;
+    const bool pre_low = (cfg->tuning & GS_TUNE_PRE_OCC6) != 0;
     for (bool &v : ctx->ev_valid) v = false;
     ctx->stats.kernel_launches = 0;
 
@@ -669,7 +669,7 @@ extern "C" int gs_backward(GsContext *ctx, const GsConfig *cfg, const GsInputs *
     }
     {
         StageTimer t(ctx, GS_STAGE_PREPROCESS_BWD, st);
-        rc = launch_preprocess_bwd(c, di, *saved, acc, *gin, st, (cfg->tuning & GS_TUNE_PBWD_V1) ? 1 : 0);
+        rc = launch_preprocess_bwd(c, di, *saved, acc, *gin, st, (cfg->tuning & GS_TUNE_PBWD_2PHASE) ? 1 : 0);
         if (rc != GS_OK) return rc;
     }
     ctx->stats.kernel_launches += 2;  // k_composite_bwd, k_preprocess_bwd

@@ -70,7 +70,7 @@ struct PreEmit {
 };
 int launch_preprocess(const DevCfg &c, const DevInputs &in, float4 *rec0, float4 *rec1, float4 *rec2, uint8_t *meta,
                       int32_t *radii, ushort4 *rects, const PreEmit &emit, cudaStream_t st, int g_begin = 0,
-                      int g_end = -1 /* = P */, bool low_occupancy = false /* 96 registers, 5 CTAs/SM (GS_TUNE_PRE_OCC5) */);
+                      int g_end = -1 /* = P */, bool more_ctas = false /* 80 registers, 6 CTAs/SM (GS_TUNE_PRE_OCC6) */);
 int launch_mark_visible(const DevCfg &c, const float *means3D, uint8_t *present, cudaStream_t st);
 
 // binning (gs_binning.cu)
@@ -109,7 +109,7 @@ int launch_composite_bwd(const DevCfg &c, const GsSaved &s, const float *dL_dcol
                          float *grad_acc /* [V*P*GS_ACC_STRIDE], zeroed */, cudaStream_t st,
                          int variant = 0 /* 1: the round-1 kernel (GS_TUNE_BWD_V1) */);
 int launch_preprocess_bwd(const DevCfg &c, const DevInputs &in, const GsSaved &s, const float *grad_acc,
-                          const GsInGrads &g, cudaStream_t st, int variant = 0 /* 1: the round-1 kernel (GS_TUNE_PBWD_V1) */);
+                          const GsInGrads &g, cudaStream_t st, int variant = 0 /* 1: the two-phase kernel (GS_TUNE_PBWD_2PHASE) */);
 
 // per (view,Gaussian) accumulator written by the composite backward:
 //   0-2 dL/drgb, 3-4 dL/dmean2D (NDC-scaled), 5-7 dL/dconic (a, b stored once, c), 8 dL/dopacity, 9 dL/dz

@@ -127,7 +127,8 @@ __device__ __forceinline__ void project_splat(const DevCfg &c, const ViewCam &ca
 }
 
 // MINB: resident CTAs per SM the register allocation is bounded for.  Unbounded the kernel takes 96 registers (5 CTAs/SM,
-// 28 % occupancy; ncu: issue slots 50 % busy, latency-bound); 8 bounds it to 64 registers (116 bytes of spills).
+// 28 % occupancy; ncu: issue slots 50 % busy, latency-bound).  Measured on C2 with the 16-coefficient staging: 96
+// registers 0.222 ms; bounded to 64 (8 CTAs/SM, 44 % occupancy, 116 bytes of spills = +15 % instructions) 0.275 ms.
 template <bool HAS_SH, int MINB>
 __global__ void __launch_bounds__(PRE_THREADS, MINB)
 k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, float4 *__restrict__ rec1,
@@ -321,7 +322,7 @@ __global__ void k_mark_visible(const DevCfg c, const float *__restrict__ means3D
 
 int launch_preprocess(const DevCfg &c, const DevInputs &in, float4 *rec0, float4 *rec1, float4 *rec2, uint8_t *meta,
                       int32_t *radii, ushort4 *rects, const PreEmit &emit, cudaStream_t st, int g_begin, int g_end,
-                      bool low_occupancy) {
+                      bool more_ctas) {
     if (g_end < 0) g_end = c.P;
     if (g_end <= g_begin) return GS_OK;
     dim3 grid((g_end - g_begin + PRE_THREADS - 1) / PRE_THREADS, c.S);
@@ -332,8 +333,8 @@ int launch_preprocess(const DevCfg &c, const DevInputs &in, float4 *rec0, float4
         return GS_OK;
     };
     int rc;
-    if (in.shs) rc = low_occupancy ? launch(k_preprocess<true, 5>) : launch(k_preprocess<true, 8>);
-    else rc = low_occupancy ? launch(k_preprocess<false, 5>) : launch(k_preprocess<false, 8>);
+    if (in.shs) rc = more_ctas ? launch(k_preprocess<true, 6>) : launch(k_preprocess<true, 5>);
+    else rc = more_ctas ? launch(k_preprocess<false, 6>) : launch(k_preprocess<false, 5>);
     if (rc != GS_OK) return rc;
     GS_CUDA_OK(cudaGetLastError());
     return GS_OK;

@@ -79,7 +79,7 @@ __device__ __forceinline__ void sh_backward_channel(int deg, const float *sh, fl
 
 template <bool HAS_SH, int MINB>
 __global__ void __launch_bounds__(PB_THREADS, MINB)
-k_preprocess_bwd_v1(const DevCfg c, const DevInputs in, const uint8_t *__restrict__ meta, const float *__restrict__ acc,
+k_preprocess_bwd(const DevCfg c, const DevInputs in, const uint8_t *__restrict__ meta, const float *__restrict__ acc,
                     const GsInGrads g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PbSmem *sm = reinterpret_cast<PbSmem *>(smem_raw);
@@ -330,7 +330,7 @@ k_preprocess_bwd_v1(const DevCfg c, const DevInputs in, const uint8_t *__restric
 
 
 // ---------------------------------------------------------------------------------------------------------
-// v2 (round 2): two phases per thread instead of one
+// Round-2 experiment (GS_TUNE_PBWD_2PHASE; measured SLOWER, kept for the A/B): two phases per thread instead of one
 // ---------------------------------------------------------------------------------------------------------
 // v1 carried the 48 SH-gradient accumulators through the whole geometry chain: 150 registers unbounded, 128 bounded,
 // 18-23 % occupancy, issue slots 56 % busy (latency-bound).  The SH gradient is linear in (basis(dir_v) x dL/dcolour_v)
@@ -341,11 +341,14 @@ k_preprocess_bwd_v1(const DevCfg c, const DevInputs in, const uint8_t *__restric
 //             loop over the views is done and are overwritten in place by its gradients
 // Only the 16 coefficients per channel the evaluator can touch are staged (192 instead of 300 bytes per thread).  The
 // gradient rows leave by ONE bulk TMA store when M <= 16, else by coalesced stores that append the zero bands.
+// Result on C2: 80 registers, 35 % occupancy (single pass: 128 registers, 23 %), issue slots 69 % busy (56 %) -- but 213 M
+// warp-instructions instead of 137 M (the per-view camera / direction / basis work is redone per phase): 0.271 ms
+// against 0.220 ms.  The single-pass kernel stays the default.
 constexpr int PB2_MIN_CTAS = 6;
 
 template <bool HAS_SH>
 __global__ void __launch_bounds__(PB_THREADS, PB2_MIN_CTAS)
-k_preprocess_bwd(const DevCfg c, const DevInputs in, const uint8_t *__restrict__ meta, const float *__restrict__ acc,
+k_preprocess_bwd_2phase(const DevCfg c, const DevInputs in, const uint8_t *__restrict__ meta, const float *__restrict__ acc,
                  const GsInGrads g) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PbSmem *sm = reinterpret_cast<PbSmem *>(smem_raw);
@@ -626,20 +629,20 @@ int launch_preprocess_bwd(const DevCfg &c, const DevInputs &in, const GsSaved &s
                           const GsInGrads &g, cudaStream_t st, int variant) {
     if (c.P == 0) return GS_OK;
     dim3 grid((c.P + PB_THREADS - 1) / PB_THREADS, c.S);
-    if (variant == 1) {  // the round-1 kernel (GS_TUNE_PBWD_V1)
+    if (variant != 1) {  // single pass over the views (default)
         if (in.shs) {
             size_t smem = PB_SMEM_HDR + (size_t)PB_THREADS * c.M * 12;
-            GS_CUDA_OK(cudaFuncSetAttribute(k_preprocess_bwd_v1<true, PB_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_preprocess_bwd_v1<true, PB_MIN_CTAS><<<grid, PB_THREADS, smem, st>>>(c, in, s.meta, grad_acc, g);
+            GS_CUDA_OK(cudaFuncSetAttribute(k_preprocess_bwd<true, PB_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_preprocess_bwd<true, PB_MIN_CTAS><<<grid, PB_THREADS, smem, st>>>(c, in, s.meta, grad_acc, g);
         } else {
-            k_preprocess_bwd_v1<false, PB_MIN_CTAS><<<grid, PB_THREADS, PB_SMEM_HDR, st>>>(c, in, s.meta, grad_acc, g);
+            k_preprocess_bwd<false, PB_MIN_CTAS><<<grid, PB_THREADS, PB_SMEM_HDR, st>>>(c, in, s.meta, grad_acc, g);
         }
     } else if (in.shs) {
         size_t smem = PB_SMEM_HDR + (size_t)PB_THREADS * (c.M <= PB_SH_EVAL ? c.M * 3 : PB_SH_EVAL * 3 + 1) * 4;
-        GS_CUDA_OK(cudaFuncSetAttribute(k_preprocess_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_preprocess_bwd<true><<<grid, PB_THREADS, smem, st>>>(c, in, s.meta, grad_acc, g);
+        GS_CUDA_OK(cudaFuncSetAttribute(k_preprocess_bwd_2phase<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_preprocess_bwd_2phase<true><<<grid, PB_THREADS, smem, st>>>(c, in, s.meta, grad_acc, g);
     } else {
-        k_preprocess_bwd<false><<<grid, PB_THREADS, PB_SMEM_HDR, st>>>(c, in, s.meta, grad_acc, g);
+        k_preprocess_bwd_2phase<false><<<grid, PB_THREADS, PB_SMEM_HDR, st>>>(c, in, s.meta, grad_acc, g);
     }
     GS_CUDA_OK(cudaGetLastError());
     return GS_OK;
