@@ -396,12 +396,38 @@ def main():
                 return rasterize_batch(bs4, d4["means3D"], d4["opacities"], shs=d4["shs"], cov3D_precomp=d4["cov3D_precomp"])
 
         steps4 = max(3, args.steps // 4)
-        ms4 = timed(fwd4, steps4, 3)
+        state4 = {"exact": 0, "calls": 0}
+
+        def fwd4_counted():
+            fwd4()
+            state4["calls"] += 1
+            state4["exact"] += int(rasterizer.last_stats(dev)["speculative"] == 0)
+
+        for _ in range(3):
+            fwd4()                      # exact -> trial -> steady state
+        ms4 = timed(fwd4_counted, steps4, 3)
         st4 = rasterizer.last_stats(dev)
+        # per-rank view of the same loop (its own CUDA events), gathered: who is the slowest and why
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record(stream)
+        for _ in range(steps4):
+            fwd4()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        mine = torch.tensor([e0.elapsed_time(e1) / steps4, float(st4["num_rendered"]), float(st4["speculative"]),
+                             float(state4["exact"])], device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(allr, mine)
+        else:
+            allr = [mine]
         c4 = {"workload": WORKLOADS["c4"][3], "scaling": "strong", "views_total": V4, "views_per_gpu": len(mine4),
               "steps": steps4, "ms_per_step": ms4 / steps4, "views_per_sec_512": V4 * steps4 / (ms4 * 1e-3),
               "gaussians_per_sec": P4 * V4 * steps4 / (ms4 * 1e-3), "tile_instances_rank0": st4["num_rendered"],
-              "speculative": st4["speculative"]}
+              "speculative": st4["speculative"],
+              "per_rank": [{"ms_per_step": float(t[0]), "tile_instances": int(t[1]), "speculative": int(t[2]),
+                            "exact_path_calls_in_timed_loop": int(t[3])} for t in allr]}
         del d4, bs4
         torch.cuda.empty_cache()
         rasterizer.trim_memory(dev)

@@ -98,8 +98,8 @@ k_tile_scan(int nvt, const uint32_t *__restrict__ counters, uint32_t *__restrict
 __global__ void k_emit_buckets(const DevCfg c, const float4 *__restrict__ rec0, const float4 *__restrict__ rec1,
                                const float4 *__restrict__ rec2, const ushort4 *__restrict__ rects,
                                const uint32_t *__restrict__ offsets, const uint32_t sub_cap,
-                               const float *__restrict__ strata, uint32_t *__restrict__ cursor,
-                               uint64_t *__restrict__ bucket) {
+                               const float *__restrict__ strata, const int strata_per_tile,
+                               uint32_t *__restrict__ cursor, uint64_t *__restrict__ bucket) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (size_t)c.V * c.P) return;
     const ushort4 r = rects[g];
@@ -110,7 +110,7 @@ __global__ void k_emit_buckets(const DevCfg c, const float4 *__restrict__ rec0, 
     const uint64_t key = ((uint64_t)__float_as_uint(q2.y) << 32) | i;
     const uint32_t tbase = v * (uint32_t)c.ntiles;
     uint32_t sub = i & (BIN_SUB - 1);
-    if (strata) {  // sub-bucket = depth stratum of this view (same rule as k_preprocess)
+    if (strata && !strata_per_tile) {  // sub-bucket = depth stratum of this view (same rule as k_preprocess)
         sub = 0;
 #pragma unroll
         for (int q = 0; q < BIN_SUB - 1; q++) sub += q2.y >= strata[(size_t)v * BIN_SUB + q] ? 1u : 0u;
@@ -127,7 +127,9 @@ __global__ void k_emit_buckets(const DevCfg c, const float4 *__restrict__ rec0, 
 #pragma unroll
         for (int k = 0; k < BATCH; k++) {
             ok[k] = cy < (int)r.w && gs_tile_reached(q0, q1, q2, cx, cy);  // same predicate as the count in k_preprocess
-            slot[k] = (size_t)(tbase + (uint32_t)(cy * c.gx + cx)) * BIN_SUB + sub;
+            const uint32_t tile = tbase + (uint32_t)(cy * c.gx + cx);
+            const uint32_t subk = (strata_per_tile && ok[k]) ? gs_tile_stratum(strata, tile, q2.y) : sub;
+            slot[k] = (size_t)tile * BIN_SUB + subk;
             if (++cx == (int)r.z) {
                 cx = r.x;
                 cy++;
@@ -377,13 +379,13 @@ size_t bin_scratch_bytes(const DevCfg &c, int64_t D, bool fast) {
 }
 
 int bin_emit_fast(const DevCfg &c, int64_t D, const float4 *rec0, const float4 *rec1, const float4 *rec2,
-                  const ushort4 *rects, const uint32_t *offsets, uint32_t sub_cap, const float *strata, uint32_t *cursor,
-                  void *scratch, cudaStream_t st) {
+                  const ushort4 *rects, const uint32_t *offsets, uint32_t sub_cap, const float *strata, int strata_per_tile,
+                  uint32_t *cursor, void *scratch, cudaStream_t st) {
     if (D <= 0) return GS_OK;
     GS_CUDA_OK(cudaMemsetAsync(cursor, 0, bin_counter_bytes(c), st));
     const size_t n = (size_t)c.V * c.P;
-    k_emit_buckets<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c, rec0, rec1, rec2, rects, offsets, sub_cap, strata, cursor,
-                                                                 static_cast<uint64_t *>(scratch));
+    k_emit_buckets<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c, rec0, rec1, rec2, rects, offsets, sub_cap, strata,
+                                                                 strata_per_tile, cursor, static_cast<uint64_t *>(scratch));
     GS_CUDA_OK(cudaGetLastError());
     return GS_OK;
 }
@@ -547,7 +549,8 @@ constexpr int RS_WARPS = 4;          // strata per CTA (independent warps)
 __global__ void __launch_bounds__(RS_WARPS * 32)
 k_stratum_rank_sort(uint32_t nvt, uint32_t sub_cap, uint32_t cap_pad, const uint32_t *__restrict__ cursor,
                     const uint64_t *__restrict__ bucket, uint32_t *__restrict__ point_list, uint2 *__restrict__ ranges,
-                    uint32_t *__restrict__ acc, uint32_t *__restrict__ info) {
+                    uint32_t *__restrict__ acc, uint32_t *__restrict__ info, const float4 *__restrict__ rec2, uint32_t P,
+                    uint32_t ntiles, float *__restrict__ next) {
     extern __shared__ __align__(16) unsigned char rs_smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t sidx = blockIdx.x * RS_WARPS + warp;   // (view, tile, stratum)
@@ -578,6 +581,11 @@ k_stratum_rank_sort(uint32_t nvt, uint32_t sub_cap, uint32_t cap_pad, const uint
             }
         }
     }
+    // Per-tile mode: this call's sorted lists define the boundaries of the NEXT call (row vt of `next`): entry q is the
+    // depth of the list element at position total (q+1) / BIN_SUB, written by the warp whose stratum holds that position
+    // (below); entries nobody owns (empty tile, the unused eighth) are +inf.
+    if (next && k == 0 && lane < BIN_SUB && (total == 0 || lane == BIN_SUB - 1))
+        next[(size_t)vt * BIN_SUB + lane] = __int_as_float(0x7f800000);
     if (n == 0) return;
     const uint64_t *__restrict__ src = bucket + (size_t)sidx * sub_cap;
     uint64_t *srt = reinterpret_cast<uint64_t *>(rs_smem) + (size_t)warp * cap_pad;
@@ -677,6 +685,42 @@ k_stratum_rank_sort(uint32_t nvt, uint32_t sub_cap, uint32_t cap_pad, const uint
         for (uint32_t q = 0; q < bn; q++) rank += srt[bs + q] < key ? 1u : 0u;  // keys are distinct: (depth, index)
         if (valid) dst[bs + rank] = (uint32_t)key;
     }
+    if (next) {
+        __syncwarp();  // the list segment written above is visible to every lane of this warp
+        if (lane < BIN_SUB - 1) {
+            const uint32_t pos = (uint32_t)(((uint64_t)total * (lane + 1)) / BIN_SUB);
+            if (pos >= below && pos < below + n)
+                next[(size_t)vt * BIN_SUB + lane] = rec2[(size_t)(vt / ntiles) * P + dst[pos - below]].y;
+        }
+    }
+}
+
+// per-tile boundaries from the sorted lists of an exact-path call: thread (tile, q) reads the depth of the entry at the
+// (q+1)-th octile of the tile's list
+__global__ void k_tile_octiles(const DevCfg c, const uint32_t *__restrict__ point_list, const uint2 *__restrict__ ranges,
+                               const float4 *__restrict__ rec2, float *__restrict__ table) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nvt = (size_t)c.V * c.ntiles;
+    if (g >= nvt * BIN_SUB) return;
+    const size_t vt = g / BIN_SUB;
+    const uint32_t q = (uint32_t)(g % BIN_SUB);
+    const uint2 r = ranges[vt];
+    const uint32_t n = r.y - r.x;
+    float b = __int_as_float(0x7f800000);
+    if (n > 0 && q < BIN_SUB - 1) {
+        const uint32_t pos = r.x + (uint32_t)(((uint64_t)n * (q + 1)) / BIN_SUB);
+        b = rec2[(vt / c.ntiles) * (size_t)c.P + point_list[pos]].y;
+    }
+    table[g] = b;
+}
+
+int bin_learn_tile_strata(const DevCfg &c, const uint32_t *point_list, const uint2 *ranges, const float4 *rec2, float *table,
+                          cudaStream_t st) {
+    const size_t n = (size_t)c.V * c.ntiles * BIN_SUB;
+    if (n == 0) return GS_OK;
+    k_tile_octiles<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c, point_list, ranges, rec2, table);
+    GS_CUDA_OK(cudaGetLastError());
+    return GS_OK;
 }
 
 template <int THREADS, int MAX_ITEMS>
@@ -691,8 +735,9 @@ int launch_stratum_sort(int nvt, uint32_t sub_cap, const uint32_t *cursor, const
 }
 
 int bin_sort_strata(const DevCfg &c, uint32_t sub_cap, const uint32_t *cursor, const void *bucket, uint32_t *point_list,
-                    uint2 *ranges, uint32_t *acc, uint32_t *info, cudaStream_t st, bool merge_sort) {
-    if (!merge_sort) {
+                    uint2 *ranges, uint32_t *acc, uint32_t *info, cudaStream_t st, bool merge_sort, const float4 *rec2,
+                    float *next_tile_strata) {
+    if (!merge_sort || next_tile_strata) {   // (the merge-sort kernel does not refresh per-tile boundaries)
         // hand-written warp-per-stratum distribution sort (default)
         if (sub_cap > BIN_STRATUM_CAP) return gs_set_error(GS_ERR_INVALID, "stratum capacity beyond the sort's");
         const uint32_t nvt = (uint32_t)c.V * (uint32_t)c.ntiles;
@@ -705,7 +750,8 @@ int bin_sort_strata(const DevCfg &c, uint32_t sub_cap, const uint32_t *cursor, c
         }
         const uint32_t ctas = (nvt * BIN_SUB + RS_WARPS - 1) / RS_WARPS;
         k_stratum_rank_sort<<<ctas, RS_WARPS * 32, smem, st>>>(nvt, sub_cap, cap_pad, cursor, static_cast<const uint64_t *>(bucket),
-                                                               point_list, ranges, acc, info);
+                                                               point_list, ranges, acc, info, rec2, (uint32_t)c.P, (uint32_t)c.ntiles,
+                                                               next_tile_strata);
         GS_CUDA_OK(cudaGetLastError());
         return GS_OK;
     }
@@ -722,7 +768,11 @@ int bin_sort_strata(const DevCfg &c, uint32_t sub_cap, const uint32_t *cursor, c
     return launch_stratum_sort<THREADS, 16>(nvt, sub_cap, cursor, b, point_list, ranges, acc, info, st);
 }
 
-size_t bin_strata_bytes(const DevCfg &c) { return (size_t)c.V * BIN_SUB * 4 + (size_t)c.V * STRATA_BINS * 4; }
+size_t bin_strata_bytes(const DevCfg &c) {
+    const size_t per_view = (size_t)c.V * BIN_SUB * 4 + (size_t)c.V * STRATA_BINS * 4;
+    const size_t per_tile = 2 * (size_t)c.V * c.ntiles * BIN_SUB * 4;  // two tables: this call's and the next one's
+    return per_view > per_tile ? per_view : per_tile;
+}
 
 int bin_learn_strata(const DevCfg &c, const ushort4 *rects, const float4 *rec2, void *strata_buf, cudaStream_t st) {
     float *strata = static_cast<float *>(strata_buf);

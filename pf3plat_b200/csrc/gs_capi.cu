@@ -79,6 +79,11 @@ struct GsContext {
         // tries strata with doubled capacities.  ON: strata with capacities learned from stratified counts.
         // OFF: the trial overflowed (a tile whose depths crowd into one stratum): this shape stays on whole-tile sorts.
         int strata_state = STRATA_UNKNOWN;
+        // Which boundaries `strata` holds: one row per view (octiles of the view's depths), or -- for shapes whose
+        // per-view trial overflowed: tiles that each see a narrow depth range, e.g. PF3plat's pixel-aligned Gaussians on
+        // a smooth surface -- one row per (view, tile), learned from the exact call's sorted lists and refreshed by the
+        // stratum sort of every call (two tables, swapped on success).
+        int strata_per_tile = 0, want_per_tile = 0, tile_tab = 0;
     } spec;
     GrowBuf strata;        // [V][BIN_SUB] stratum boundaries + histogram scratch
     cudaEvent_t ev_pre = nullptr;   // "preprocess done" (speculative path: lets the radii copy start early)
@@ -210,7 +215,10 @@ void learn_capacities(GsContext *ctx, const DevCfg &c, uint32_t max_tile, uint32
         ctx->spec.sub_cap = 0;  // lists too long for the shared-memory sort (or offsets beyond 32 bits): exact path
         return;
     }
-    if (ctx->spec.V != c.V || ctx->spec.ntiles != c.ntiles) ctx->spec.strata_state = STRATA_UNKNOWN;
+    if (ctx->spec.V != c.V || ctx->spec.ntiles != c.ntiles) {
+        ctx->spec.strata_state = STRATA_UNKNOWN;
+        ctx->spec.strata_per_tile = ctx->spec.want_per_tile = 0;
+    }
     ctx->spec.V = c.V;
     ctx->spec.ntiles = c.ntiles;
     ctx->spec.sub_cap = sub_cap;
@@ -409,7 +417,11 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
             else sub_cap = trial;
         }
         if (strata && sub_cap > BIN_STRATUM_CAP) sub_cap = BIN_STRATUM_CAP;
-        const float *strata_tab = strata ? static_cast<const float *>(ctx->strata.p) : nullptr;
+        const int per_tile = strata ? ctx->spec.strata_per_tile : 0;
+        const size_t tab_floats = nvt * BIN_SUB;  // one per-tile table
+        float *tab0 = static_cast<float *>(ctx->strata.p);
+        const float *strata_tab = !strata ? nullptr : (per_tile ? tab0 + (size_t)ctx->spec.tile_tab * tab_floats : tab0);
+        float *strata_next = (strata && per_tile) ? tab0 + (size_t)(ctx->spec.tile_tab ^ 1) * tab_floats : nullptr;
         const size_t slots = nvt * BIN_SUB;
         rc = ctx->sort.reserve(slots * sub_cap * 8, 1.0, ctx->pool, st);
         if (rc != GS_OK) return fail(rc);
@@ -426,7 +438,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
         const bool fused_emit = slots * sub_cap * 8 <= ((size_t)96 << 20) && !(cfg->tuning & GS_TUNE_SEPARATE_EMIT);
         {
             StageTimer t(ctx, GS_STAGE_PREPROCESS, st);
-            const PreEmit emit{fused_emit ? cursor : nullptr, static_cast<uint64_t *>(ctx->sort.p), sub_cap, strata_tab};
+            const PreEmit emit{fused_emit ? cursor : nullptr, static_cast<uint64_t *>(ctx->sort.p), sub_cap, strata_tab, per_tile};
             if (ctx->feed_chunks > 0) {
                 for (int k = 0; k < ctx->feed_chunks && rc == GS_OK; k++) {
                     e = cudaStreamWaitEvent(st, ctx->feed_ev[k], 0);
@@ -441,7 +453,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
         }
         if (!fused_emit) {
             StageTimer t(ctx, GS_STAGE_BIN_EMIT, st);
-            rc = bin_emit_fast(c, 1, s->rec0, s->rec1, s->rec2, rects, nullptr, sub_cap, strata_tab, cursor, ctx->sort.p, st);
+            rc = bin_emit_fast(c, 1, s->rec0, s->rec1, s->rec2, rects, nullptr, sub_cap, strata_tab, per_tile, cursor, ctx->sort.p, st);
             if (rc != GS_OK) return fail(rc);
         }
         // gs_render_host: the radii leave for the host on the copy stream as soon as they are final -- after preprocess
@@ -481,7 +493,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
             StageTimer t(ctx, GS_STAGE_BIN_SORT, st);
             if (strata) {
                 rc = bin_sort_strata(c, sub_cap, cursor, ctx->sort.p, s->point_list, s->ranges, verdict_acc, ctx->d_word, st,
-                                     (cfg->tuning & GS_TUNE_STRATA_MERGE_SORT) != 0);
+                                     (cfg->tuning & GS_TUNE_STRATA_MERGE_SORT) != 0, s->rec2, strata_next);
                 if (rc == GS_OK && (e = cudaEventRecord(ctx->ev_info, st)) != cudaSuccess)
                     return fail(gs_set_cuda_error(e, "read back binning info", __FILE__, __LINE__));
                 if (rc == GS_OK && (e = start_radii_copy()) != cudaSuccess)
@@ -519,6 +531,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
                     }
                     ctx->spec.strata_state = STRATA_ON;
                     ctx->spec.sub_cap = next;
+                    if (per_tile) ctx->spec.tile_tab ^= 1;  // the sort wrote the next call's boundaries into the other table
                 }
             } else {
                 learn_capacities(ctx, c, ctx->h_word[1], ctx->h_word[2]);
@@ -541,7 +554,15 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
         }
         // overflow: some sub-bucket or tile list outgrew its capacity.  Results are invalid; redo exactly.
         ctx->spec.sub_cap = 0;
-        if (strata) ctx->spec.strata_state = ctx->spec.strata_state == STRATA_TRIAL ? STRATA_OFF : STRATA_UNKNOWN;
+        if (strata) {
+            if (ctx->spec.strata_state == STRATA_TRIAL && !per_tile && !(cfg->tuning & GS_TUNE_NO_TILE_STRATA)) {
+                // the per-view boundaries crowd some tile into one stratum: the exact redo below learns per-tile ones
+                ctx->spec.want_per_tile = 1;
+                ctx->spec.strata_state = STRATA_UNKNOWN;
+            } else {
+                ctx->spec.strata_state = ctx->spec.strata_state == STRATA_TRIAL ? STRATA_OFF : STRATA_UNKNOWN;
+            }
+        }
         if (ctx->host_radii_dst && ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
         cudaFreeAsync(s->point_list, st);
         s->point_list = nullptr;
@@ -553,7 +574,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
         StageTimer t(ctx, GS_STAGE_PREPROCESS, st);
         cudaError_t e = cudaMemsetAsync(tile_counts, 0, bin_counter_bytes(c), st);
         if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "cudaMemsetAsync(tile_counts)", __FILE__, __LINE__));
-        const PreEmit emit{tile_counts, nullptr, 0, nullptr};  // exact path: sub-bucket = index % BIN_SUB
+        const PreEmit emit{tile_counts, nullptr, 0, nullptr, 0};  // exact path: sub-bucket = index % BIN_SUB
         for (int k = 0; k < ctx->feed_chunks; k++) {  // gs_render_host: every piece of the SH block must have landed
             e = cudaStreamWaitEvent(st, ctx->feed_ev[k], 0);
             if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "cudaStreamWaitEvent(feed)", __FILE__, __LINE__));
@@ -595,7 +616,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     {
         StageTimer t(ctx, GS_STAGE_BIN_EMIT, st);
         if (fast)
-            rc = bin_emit_fast(c, D, s->rec0, s->rec1, s->rec2, rects, sub_offsets, 0, nullptr, cursor, ctx->sort.p, st);
+            rc = bin_emit_fast(c, D, s->rec0, s->rec1, s->rec2, rects, sub_offsets, 0, nullptr, 0, cursor, ctx->sort.p, st);
         else
             rc = bin_sort_fallback(c, D, s->rec0, s->rec1, s->rec2, rects, ctx->sort.p, ctx->sort.bytes, s->point_list,
                                    s->ranges, st);
@@ -621,10 +642,16 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     if (fast && ctx->spec.sub_cap > 0 && ctx->spec.strata_state != STRATA_OFF && !(cfg->tuning & GS_TUNE_NO_STRATA) && n > 0) {
         rc = ctx->strata.reserve(bin_strata_bytes(c), 1.0, ctx->pool, st);
         if (rc != GS_OK) return fail(rc);
-        rc = bin_learn_strata(c, rects, s->rec2, ctx->strata.p, st);
+        if (ctx->spec.want_per_tile) {
+            ctx->spec.tile_tab = 0;
+            rc = bin_learn_tile_strata(c, s->point_list, s->ranges, s->rec2, static_cast<float *>(ctx->strata.p), st);
+        } else {
+            rc = bin_learn_strata(c, rects, s->rec2, ctx->strata.p, st);
+        }
         if (rc != GS_OK) return fail(rc);
         ctx->spec.strata_state = STRATA_TRIAL;
-        ctx->stats.kernel_launches += 2;  // k_depth_hist, k_strata_from_hist
+        ctx->spec.strata_per_tile = ctx->spec.want_per_tile;
+        ctx->stats.kernel_launches += ctx->spec.want_per_tile ? 1 : 2;  // k_tile_octiles | k_depth_hist, k_strata_from_hist
     }
 
     s->P = c.P; s->S = c.S; s->V = c.V; s->H = c.H; s->W = c.W;

@@ -64,10 +64,12 @@ struct PreEmit {
                           // (speculative path, fused emission); NULL = preprocess neither counts nor emits
     uint64_t *bucket;     // fused speculative emission only: fixed-capacity sub-buckets [V*tiles*BIN_SUB][sub_cap]
     uint32_t sub_cap;     // capacity of one sub-bucket (speculative path)
-    const float *strata;  // NULL: sub-bucket = index % BIN_SUB.  Else [V][BIN_SUB] ascending depth boundaries per view
-                          // (BIN_SUB - 1 used): sub-bucket = depth stratum, so that a tile's sorted list is the
-                          // concatenation of its independently sorted sub-buckets (gs_binning.cu, k_stratum_sort)
+    const float *strata;  // NULL: sub-bucket = index % BIN_SUB.  Else ascending depth boundaries (BIN_SUB - 1 used of
+                          // every BIN_SUB): sub-bucket = depth stratum, so that a tile's sorted list is the
+                          // concatenation of its independently sorted sub-buckets (gs_binning.cu)
+    int strata_per_tile;  // 0: one row of boundaries per view [V][BIN_SUB]; 1: one row per (view, tile) [V*tiles][BIN_SUB]
 };
+
 int launch_preprocess(const DevCfg &c, const DevInputs &in, float4 *rec0, float4 *rec1, float4 *rec2, uint8_t *meta,
                       int32_t *radii, ushort4 *rects, const PreEmit &emit, cudaStream_t st, int g_begin = 0,
                       int g_end = -1 /* = P */, bool more_ctas = false /* 80 registers, 6 CTAs/SM (GS_TUNE_PRE_OCC6) */);
@@ -84,15 +86,19 @@ bool bin_fits_fast_path(uint32_t max_count);
 size_t bin_scratch_bytes(const DevCfg &c, int64_t D, bool fast);
 // offsets != NULL: exact-capacity buckets at offsets[slot]; offsets == NULL: fixed-capacity buckets at slot * sub_cap
 int bin_emit_fast(const DevCfg &c, int64_t D, const float4 *rec0, const float4 *rec1, const float4 *rec2,
-                  const ushort4 *rects, const uint32_t *offsets, uint32_t sub_cap, const float *strata, uint32_t *cursor,
-                  void *scratch, cudaStream_t st);
+                  const ushort4 *rects, const uint32_t *offsets, uint32_t sub_cap, const float *strata, int strata_per_tile,
+                  uint32_t *cursor, void *scratch, cudaStream_t st);
 int bin_sort_fast(const DevCfg &c, uint32_t max_count, const uint32_t *tile_start, const uint32_t *tile_n,
                   const void *scratch, uint32_t *point_list, uint2 *ranges, cudaStream_t st);
 int bin_spec_check(const DevCfg &c, uint32_t sub_cap, uint32_t tile_limit, const uint32_t *cursor, uint32_t *info,
                    cudaStream_t st);
 int bin_sort_strata(const DevCfg &c, uint32_t sub_cap, const uint32_t *cursor, const void *bucket, uint32_t *point_list,
                     uint2 *ranges, uint32_t *acc /* 8 zeroed words */, uint32_t *info, cudaStream_t st,
-                    bool merge_sort = false /* the round-1 cub::BlockMergeSort kernel (GS_TUNE_STRATA_MERGE_SORT) */);
+                    bool merge_sort = false /* the round-1 cub::BlockMergeSort kernel (GS_TUNE_STRATA_MERGE_SORT) */,
+                    const float4 *rec2 = nullptr, float *next_tile_strata = nullptr /* per-tile mode: boundaries of the next call */);
+// per-(view, tile) stratum boundaries from the sorted lists of an exact-path call
+int bin_learn_tile_strata(const DevCfg &c, const uint32_t *point_list, const uint2 *ranges, const float4 *rec2, float *table,
+                          cudaStream_t st);
 // depth strata: per-view octiles of the depths of the binned Gaussians (weighted by their tile count), for the NEXT call
 size_t bin_strata_bytes(const DevCfg &c);          // strata table [V][BIN_SUB] floats + histogram scratch
 int bin_learn_strata(const DevCfg &c, const ushort4 *rects, const float4 *rec2, void *strata_buf, cudaStream_t st);
@@ -218,6 +224,14 @@ __device__ __forceinline__ void cov3d_from_scale_rot(const float *s, float mod, 
     c6[3] = R[1][0] * v0 * R[1][0] + R[1][1] * v1 * R[1][1] + R[1][2] * v2 * R[1][2];
     c6[4] = R[1][0] * v0 * R[2][0] + R[1][1] * v1 * R[2][1] + R[1][2] * v2 * R[2][2];
     c6[5] = R[2][0] * v0 * R[2][0] + R[2][1] * v1 * R[2][1] + R[2][2] * v2 * R[2][2];
+}
+
+// sub-bucket of depth d under one row of ascending per-(view, tile) boundaries (two 16-byte loads)
+__device__ __forceinline__ uint32_t gs_tile_stratum(const float *__restrict__ table, uint32_t tile, float d) {
+    const float4 *tb = reinterpret_cast<const float4 *>(table) + (size_t)tile * (BIN_SUB / 4);
+    const float4 b0 = __ldg(tb), b1 = __ldg(tb + 1);
+    return (uint32_t)(d >= b0.x) + (uint32_t)(d >= b0.y) + (uint32_t)(d >= b0.z) + (uint32_t)(d >= b0.w) + (uint32_t)(d >= b1.x) +
+           (uint32_t)(d >= b1.y) + (uint32_t)(d >= b1.z);
 }
 
 #define GS_LOG2E 1.4426950408889634f

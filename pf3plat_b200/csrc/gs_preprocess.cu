@@ -230,7 +230,7 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
         const int nv = min(GS_CAM_CHUNK, c.VPS - v0);
         __syncthreads();
         load_view_cams(c, scene * c.VPS + v0, nv, sm->cams);
-        if (emit.strata)
+        if (emit.strata && !emit.strata_per_tile)
             for (int t = tid; t < nv * BIN_SUB; t += PRE_THREADS)
                 sm->strata[t / BIN_SUB][t % BIN_SUB] = emit.strata[(size_t)(scene * c.VPS + v0) * BIN_SUB + t];
         __syncthreads();
@@ -258,7 +258,7 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
                 const int w = sp.rect.z - sp.rect.x, nt = w * (sp.rect.w - sp.rect.y);
                 const uint32_t tbase = (uint32_t)v * (uint32_t)c.ntiles;
                 uint32_t sub = (uint32_t)i & (BIN_SUB - 1);
-                if (emit.strata) {
+                if (emit.strata && !emit.strata_per_tile) {
                     sub = 0;
 #pragma unroll
                     for (int q = 0; q < BIN_SUB - 1; q++) sub += sp.r2.y >= sm->strata[vi][q] ? 1u : 0u;
@@ -277,7 +277,11 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
 #pragma unroll
                         for (int k = 0; k < EMIT_BATCH; k++) {
                             ok[k] = cy < (int)sp.rect.w && gs_tile_reached(sp.r0, sp.r1, sp.r2, cx, cy);
-                            slot[k] = (tbase + (uint32_t)(cy * c.gx + cx)) * BIN_SUB + sub;
+                            const uint32_t tile = tbase + (uint32_t)(cy * c.gx + cx);
+                            // per-tile boundaries (clouds whose tiles each see a narrow depth range): the candidate
+                            // tile's own eight floats decide the stratum
+                            const uint32_t subk = (emit.strata_per_tile && ok[k]) ? gs_tile_stratum(emit.strata, tile, sp.r2.y) : sub;
+                            slot[k] = tile * BIN_SUB + subk;
                             if (++cx == (int)sp.rect.z) {
                                 cx = sp.rect.x;
                                 cy++;
