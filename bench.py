@@ -195,8 +195,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback exists)"
     torch.cuda.set_device(local)
-    from pf3plat_b200.sharding import SharedCloudUploader, bind_to_gpu_numa_node
-    numa_cpus = bind_to_gpu_numa_node(local) if world > 1 else []   # before the pinned buffers are allocated (first touch)
+    from pf3plat_b200.sharding import SharedCloudUploader, numa_local_allocation
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -214,7 +213,13 @@ def main():
         "viewmatrix": vb.viewmatrix, "projmatrix": vb.projmatrix, "campos": vb.campos, "bg": sc.background,
         "tanfov": vb.tanfov,
     }
-    host = {k: v.contiguous().float().pin_memory() for k, v in host.items()}
+    # pinned staging buffers are allocated while the process sits on the GPU's own socket (first touch), then the
+    # affinity is released again
+    with numa_local_allocation(local) as numa:
+        host = {k: v.contiguous().float().pin_memory() for k, v in host.items()}
+        out_color = torch.empty((VIEWS, 3, HW, HW), dtype=torch.float32).pin_memory()
+        out_radii = torch.empty((VIEWS, P_GAUSS), dtype=torch.int32).pin_memory()
+    numa_cpus = numa.cpus
     d = {k: v.to(dev) for k, v in host.items()}
     bs = BatchSettings(image_height=HW, image_width=HW, viewmatrix=d["viewmatrix"], projmatrix=d["projmatrix"],
                        campos=d["campos"], bg=d["bg"], sh_degree=4, tanfov=d["tanfov"], tuning=args.tuning)
@@ -237,8 +242,6 @@ def main():
 
     # ---- e2e through the C ABI with HOST buffers ----
     L = _capi.lib()
-    out_color = torch.empty((VIEWS, 3, HW, HW), dtype=torch.float32).pin_memory()
-    out_radii = torch.empty((VIEWS, P_GAUSS), dtype=torch.int32).pin_memory()
     hcfg = _capi.GsConfig()
     hcfg.P, hcfg.S, hcfg.V, hcfg.M, hcfg.sh_degree = P_GAUSS, 1, VIEWS, D_SH, 4
     hcfg.image_height = hcfg.image_width = HW
@@ -597,7 +600,7 @@ def main():
                     "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "gs_render_host (C ABI, pinned host buffers)" if world == 1 else
                            "SharedCloudUploader (1/N of the cloud per rank over PCIe + NCCL all-gather over NVLink) + "
-                           "rasterize_batch + D2H of the results; ranks bound to their GPU's NUMA node",
+                           "rasterize_batch + D2H of the results; pinned buffers allocated on the GPU's NUMA node",
                     "numa_cpus_rank0": len(numa_cpus)},
             "fwd_bwd": {"value": gauss_per_step * args.steps / (ms_fb * 1e-3), "unit": "Gaussians/s",
                         "ms_per_step": ms_fb / args.steps, "loss": "MSE to U(0,1) target"},

@@ -94,10 +94,37 @@ class SharedCloudUploader:
         return out
 
 
+class numa_local_allocation:
+    """Context manager: while it is active the process runs on the CPUs NVML reports as local to the GPU, so that the
+    pinned host buffers allocated inside it (first touch) land in that socket's memory -- on an 8-GPU box GPUs 0-3 and 4-7
+    hang off different sockets, and a rank that stages its uploads in the other socket's memory pays the inter-socket hop on
+    every copy.  The previous affinity is restored on exit: the process itself stays free to run wherever the host has an
+    idle core (pinning the CPUs for good was measured to hurt on a shared host: a rank confined to a busy socket enqueues
+    its launches late)."""
+
+    def __init__(self, device_index: int):
+        self.device_index, self.saved, self.cpus = device_index, None, []
+
+    def __enter__(self):
+        try:
+            self.saved = os.sched_getaffinity(0)
+        except (AttributeError, OSError):
+            return self
+        self.cpus = bind_to_gpu_numa_node(self.device_index)
+        return self
+
+    def __exit__(self, *exc):
+        if self.saved is not None and self.cpus:
+            try:
+                os.sched_setaffinity(0, self.saved)
+            except OSError:
+                pass
+        return False
+
+
 def bind_to_gpu_numa_node(device_index: int) -> list:
     """Pins this process (and so the pinned host buffers it allocates afterwards: first touch) to the CPUs NVML reports as
-    local to the GPU -- on an 8-GPU box GPUs 0-3 and 4-7 hang off different sockets, and a rank that stages its uploads in
-    the other socket's memory pays the inter-socket hop on every copy.  Returns the CPU list in effect ([] = unchanged)."""
+    local to the GPU.  Returns the CPU list in effect ([] = unchanged).  See numa_local_allocation."""
     try:
         import pynvml
         pynvml.nvmlInit()
