@@ -343,8 +343,12 @@ def main():
         base = sc.means
         for k in range(nvar):
             m = base + torch.randn(P_GAUSS, 3, generator=g) * (base[:, 2:3] * px_at_depth) * torch.tensor([1.0, 1.0, 0.0])
+            # re-drawn Gaussians get a new position in the image at their OWN depth (their world-space size was drawn for
+            # that depth: moving one from depth 20 to depth 1.5 would make it a 13x larger splat, a different workload)
             redraw = torch.rand(P_GAUSS, generator=g) < 0.05
-            m[redraw] = base[torch.randperm(P_GAUSS, generator=g)[: int(redraw.sum())]]
+            nr = int(redraw.sum())
+            z = base[redraw, 2:3]
+            m[redraw] = torch.cat([(torch.rand(nr, 2, generator=g) * 2.1 - 1.05) * (0.5 / 0.86) * z, z], dim=1)
             variants.append(m.reshape(1, P_GAUSS, 3).contiguous().to(dev))
         state = {"k": 0, "overflows": 0, "calls": 0}
 
@@ -370,7 +374,7 @@ def main():
                   "ms_per_step": ms_mov / args.steps, "value": gauss_per_step * args.steps / (ms_mov * 1e-3),
                   "unit": "Gaussians/s", "overflow_rate": state["overflows"] / max(1, state["calls"]),
                   "calls": state["calls"], "variants": nvar,
-                  "perturbation": "means jittered by N(0, 1 px) in x/y, 5 % of the Gaussians moved to another Gaussian's position, every step"}
+                  "perturbation": "means jittered by N(0, 1 px) in x/y, 5 % of the Gaussians re-drawn at a new image position (same depth), every step"}
         del variants
         fwd()    # back to the static cloud's capacities for the stage profile below
         fwd()
