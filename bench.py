@@ -553,7 +553,8 @@ def main():
             s_["achieved_gbs"] = s_["bytes"] / (s_["ms"] * 1e-3) / 1e9 if s_["ms"] else None
             s_["frac"] = s_["achieved_gbs"] / hbm if s_["ms"] else None
         # dominant single KERNEL of the forward (bin_scan also contains the host read-back, so it is not a candidate)
-        sort_kernel = {0: "k_tile_sort", 1: "k_tile_sort_spec", 2: "k_stratum_sort"}[stats_fb["speculative"]]
+        sort_kernel = {0: "k_tile_sort", 1: "k_tile_sort_spec",
+                       2: "k_stratum_sort" if (args.tuning & 64) else "k_stratum_rank_sort"}[stats_fb["speculative"]]
         kern_ms = {"k_preprocess": stage.get("preprocess"), "k_emit_buckets": stage.get("bin_emit"),
                    sort_kernel: stage.get("bin_sort"), "k_composite_fwd": stage.get("composite")}
         kern_bytes = {"k_preprocess": b_pre, "k_emit_buckets": 12 * D_alg, sort_kernel: 24 * D_alg, "k_composite_fwd": b_comp,

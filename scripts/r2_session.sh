@@ -12,6 +12,7 @@ ab) for t in ${AB_TUNINGS:-0 64 32 16}; do GS_TUNING=$t timeout 300 python scrip
 ncu) timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__thread_inst_executed_per_inst_executed.ratio,sm__issue_active.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"k_composite|k_preprocess|k_stratum|k_tile_sort" -s 25 -c 10 --csv --log-file gpurun_out/ncu_light_$tag.csv env GS_STEPS=8 python scripts/profile_step.py > gpurun_out/ncu_light_$tag.log 2>&1; echo "ncu rc=$?" ;;
 abc4) for t in ${AB_TUNINGS:-0 32 64}; do GS_TUNING=$t GS_P=2000000 GS_V=32 GS_HW=512 GS_STEPS=6 timeout 400 python scripts/stage_times.py > gpurun_out/stages_c4_${tag}_t$t.log 2>&1; echo "C4 tuning $t:"; tail -2 gpurun_out/stages_c4_${tag}_t$t.log; done ;;
 abc5) for t in ${AB_TUNINGS:-0 32 64}; do GS_TUNING=$t GS_SCENE=aligned GS_V=3 GS_HW=256 GS_STEPS=20 timeout 300 python scripts/stage_times.py > gpurun_out/stages_c5_${tag}_t$t.log 2>&1; echo "C5-shape tuning $t:"; tail -2 gpurun_out/stages_c5_${tag}_t$t.log; done ;;
+launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 60 --csv --log-file gpurun_out/launches_$tag.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-c4 --no-moving > gpurun_out/launches_$tag.log 2>&1; echo "launches rc=$?" ;;
 probe) timeout 120 scripts/probes/pcie_pull_probe > gpurun_out/pcie_probe_$tag.log 2>&1; cat gpurun_out/pcie_probe_$tag.log ;;
 esac
 done
