@@ -6,7 +6,8 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from pf3plat_b200._capi import GS_TUNE_FORCE_RADIX_BINNING  # noqa: E402
+from pf3plat_b200._capi import (GS_TUNE_BWD_OCC4, GS_TUNE_BWD_V1, GS_TUNE_FORCE_RADIX_BINNING, GS_TUNE_FWD_V1,  # noqa: E402
+                                GS_TUNE_PBWD_2PHASE, GS_TUNE_STRATA_MERGE_SORT)
 from pf3plat_b200.cameras import make_view_batch  # noqa: E402
 from pf3plat_b200.rasterizer import BatchSettings, rasterize_batch  # noqa: E402
 from pf3plat_b200.synthetic import make_scene  # noqa: E402
@@ -15,7 +16,11 @@ dev = torch.device("cuda:0")
 for (P, V, hw, tuning, depth, sr, sh) in [(3001, 3, (40, 56), 0, True, False, True),
                                           (777, 1, (16, 16), GS_TUNE_FORCE_RADIX_BINNING, False, True, True),
                                           (5000, 2, (33, 70), 0, True, False, False),
-                                          (130, 10, (64, 64), 0, False, False, True)]:
+                                          (130, 10, (64, 64), 0, False, False, True),
+                                          # round-2 A/B variants: round-1 compositors, merge-sorted strata, two-phase
+                                          # preprocess backward, 4-CTA backward compositor
+                                          (2500, 2, (48, 48), GS_TUNE_FWD_V1 | GS_TUNE_BWD_V1 | GS_TUNE_STRATA_MERGE_SORT, True, False, True),
+                                          (2500, 2, (48, 48), GS_TUNE_PBWD_2PHASE | GS_TUNE_BWD_OCC4, False, True, True)]:
     sc = make_scene(P, V, *hw, seed=P).to(dev)
     vb = make_view_batch(sc.extrinsics, sc.intrinsics, sc.near, sc.far)
     bs = BatchSettings(image_height=hw[0], image_width=hw[1], viewmatrix=vb.viewmatrix, projmatrix=vb.projmatrix,
@@ -33,7 +38,7 @@ for (P, V, hw, tuning, depth, sr, sh) in [(3001, 3, (40, 56), 0, True, False, Tr
     else:
         c = sc.covariances
         kw["cov3D_precomp"] = torch.stack([c[:, 0, 0], c[:, 0, 1], c[:, 0, 2], c[:, 1, 1], c[:, 1, 2], c[:, 2, 2]], -1)[None].requires_grad_(True)
-    for rep in range(3):  # exact path (learns capacities + strata), strata trial, strata on their own capacities
+    for rep in range(4):  # exact path (learns capacities + strata), strata trial, strata on their own capacities
         means.grad = None
         out = rasterize_batch(bs, means, opac, **kw)
         loss = out[0].square().mean() + (out[2].mean() if depth else 0)
@@ -41,6 +46,22 @@ for (P, V, hw, tuning, depth, sr, sh) in [(3001, 3, (40, 56), 0, True, False, Tr
         torch.cuda.synchronize()
         assert torch.isfinite(means.grad).all()
     print("ok", P, V, hw, tuning, depth, sr, sh)
+
+# ---- per-(view, tile) strata: a pixel-aligned cloud (the per-view trial overflows, the redo learns per-tile boundaries) ----
+from pf3plat_b200.render import render_views  # noqa: E402
+from pf3plat_b200.rasterizer import last_stats  # noqa: E402
+from pf3plat_b200.synthetic import make_pixel_aligned_scene  # noqa: E402
+
+sc = make_pixel_aligned_scene(64, 64, 2, seed=3).to(dev)
+states = []
+for rep in range(6):
+    m = sc.means[None].clone().requires_grad_(True)
+    col = render_views(sc.extrinsics, sc.intrinsics, sc.near, sc.far, sc.image_shape, sc.background, m, sc.covariances[None],
+                       sc.harmonics[None], sc.opacities[None])
+    col.square().mean().backward()
+    torch.cuda.synchronize()
+    states.append(last_stats(dev)["speculative"])
+print("ok pixel-aligned, speculative per call:", states)
 
 # ---- the rows next to the rasterizer: fused adapter (forward + backward), PSNR / SSIM ----
 from pf3plat_b200.adapter import GaussianAdapter, GaussianAdapterCfg  # noqa: E402
