@@ -13,6 +13,7 @@ from pf3plat_b200.rasterizer import BatchSettings, rasterize_batch  # noqa: E402
 from pf3plat_b200.synthetic import make_scene  # noqa: E402
 
 dev = torch.device("cuda:0")
+EXTRA = int(os.environ.get("GS_SAN_TUNING", "0"))   # OR-ed into every case (e.g. GS_TUNE_FWD_V1 = 32)
 for (P, V, hw, tuning, depth, sr, sh) in [(3001, 3, (40, 56), 0, True, False, True),
                                           (777, 1, (16, 16), GS_TUNE_FORCE_RADIX_BINNING, False, True, True),
                                           (5000, 2, (33, 70), 0, True, False, False),
@@ -24,7 +25,7 @@ for (P, V, hw, tuning, depth, sr, sh) in [(3001, 3, (40, 56), 0, True, False, Tr
     sc = make_scene(P, V, *hw, seed=P).to(dev)
     vb = make_view_batch(sc.extrinsics, sc.intrinsics, sc.near, sc.far)
     bs = BatchSettings(image_height=hw[0], image_width=hw[1], viewmatrix=vb.viewmatrix, projmatrix=vb.projmatrix,
-                       campos=vb.campos, bg=sc.background, sh_degree=4, tanfov=vb.tanfov, with_depth=depth, tuning=tuning)
+                       campos=vb.campos, bg=sc.background, sh_degree=4, tanfov=vb.tanfov, with_depth=depth, tuning=tuning | EXTRA)
     means = sc.means[None].clone().requires_grad_(True)
     opac = sc.opacities[None].clone().requires_grad_(True)
     kw = {}
