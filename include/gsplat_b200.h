@@ -62,7 +62,7 @@ enum {
     GS_TUNE_SEPARATE_EMIT = 4u,       /* speculative path: fill the buckets with k_emit_buckets even when they fit L2 */
     GS_TUNE_NO_STRATA = 8u,           /* speculative path: never bin by depth stratum (whole-tile sorts only) */
     GS_TUNE_BWD_V1 = 16u,             /* backward compositor: the round-1 kernel (per-pixel 10-component gradients + transpose-reduce) instead of the pair-matrix kernel (A/B) */
-    GS_TUNE_FWD_V1 = 32u,             /* forward compositor: the round-1 kernel (one CTA per tile, all-thread cp.async staging, CTA barriers) instead of the persistent warp-specialised kernel (A/B) */
+    GS_TUNE_FWD_WS = 32u,             /* forward compositor: the persistent warp-specialised kernel (producer warp + 8 consumer warps over an mbarrier ring) instead of the barrier-synchronised one-CTA-per-tile kernel (A/B: a tie on C2) */
     GS_TUNE_STRATA_MERGE_SORT = 64u,  /* stratified binning: sort the strata with the round-1 cub::BlockMergeSort kernel instead of the hand-written warp-per-stratum distribution sort (A/B) */
     GS_TUNE_BWD_OCC4 = 128u,          /* backward compositor: batches of 128 entries and 64 registers (4 CTAs/SM) instead of 256 / 80 (3 CTAs/SM) (A/B) */
     GS_TUNE_PRE_OCC6 = 4096u,         /* preprocess: registers bounded to 80 (6 CTAs/SM) instead of unbounded (96, 5 CTAs/SM) (A/B) */

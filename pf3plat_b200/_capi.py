@@ -21,7 +21,7 @@ GS_TUNE_NO_SPECULATION = 2
 GS_TUNE_SEPARATE_EMIT = 4
 GS_TUNE_NO_STRATA = 8
 GS_TUNE_BWD_V1 = 16
-GS_TUNE_FWD_V1 = 32
+GS_TUNE_FWD_WS = 32
 GS_TUNE_STRATA_MERGE_SORT = 64
 GS_TUNE_BWD_OCC4 = 128
 GS_TUNE_PRE_OCC6 = 4096

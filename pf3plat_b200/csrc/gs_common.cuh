@@ -110,7 +110,7 @@ int bin_sort_fallback(const DevCfg &c, int64_t D, const float4 *rec0, const floa
                       cudaStream_t st);
 
 int launch_composite_fwd(const DevCfg &c, const GsSaved &s, float *color, float *depth, cudaStream_t st,
-                         int variant = 0 /* 1: the round-1 kernel, one CTA per tile (GS_TUNE_FWD_V1) */);
+                         int variant = 0 /* 2: the persistent warp-specialised kernel (GS_TUNE_FWD_WS) */);
 int launch_composite_bwd(const DevCfg &c, const GsSaved &s, const float *dL_dcolor, const float *dL_ddepth,
                          float *grad_acc /* [V*P*GS_ACC_STRIDE], zeroed */, cudaStream_t st,
                          int variant = 0 /* 1: the round-1 kernel (GS_TUNE_BWD_V1) */);

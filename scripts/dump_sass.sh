@@ -8,8 +8,8 @@ dump() {  # object file, substring of the mangled name, output name
   cuobjdump -sass -fun "$f" pf3plat_b200/csrc/$1.o | grep -v "^Fatbin\|^=====\|^arch\|^code version\|^host\|^compile_size\|^$" | sed 's/ *\/\* 0x[0-9a-f]* \*\/$//' > profiles/sass/$3.sass
   echo "$3: $(grep -cE '^\s+/\*[0-9a-f]{4}\*/' profiles/sass/$3.sass) instructions"
 }
-dump gs_composite_fwd "k_composite_fwdILb0ELi5" r2_k_composite_fwd_warp_specialised
-dump gs_composite_fwd "k_composite_fwd_v1ILb0" r2_k_composite_fwd_v1
+dump gs_composite_fwd "k_composite_fwd_wsILb0" r2_k_composite_fwd_warp_specialised
+dump gs_composite_fwd "15k_composite_fwdILb0" r2_k_composite_fwd_v1
 dump gs_composite_bwd "k_composite_bwdILb0ELi256" r2_k_composite_bwd_pair_matrix
 dump gs_composite_bwd "k_composite_bwd_v1ILb0" r2_k_composite_bwd_v1
 dump gs_binning "k_stratum_rank_sort" r2_k_stratum_rank_sort

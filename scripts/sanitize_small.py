@@ -6,21 +6,21 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from pf3plat_b200._capi import (GS_TUNE_BWD_OCC4, GS_TUNE_BWD_V1, GS_TUNE_FORCE_RADIX_BINNING, GS_TUNE_FWD_V1,  # noqa: E402
+from pf3plat_b200._capi import (GS_TUNE_BWD_OCC4, GS_TUNE_BWD_V1, GS_TUNE_FORCE_RADIX_BINNING, GS_TUNE_FWD_WS,  # noqa: E402
                                 GS_TUNE_PBWD_2PHASE, GS_TUNE_STRATA_MERGE_SORT)
 from pf3plat_b200.cameras import make_view_batch  # noqa: E402
 from pf3plat_b200.rasterizer import BatchSettings, rasterize_batch  # noqa: E402
 from pf3plat_b200.synthetic import make_scene  # noqa: E402
 
 dev = torch.device("cuda:0")
-EXTRA = int(os.environ.get("GS_SAN_TUNING", "0"))   # OR-ed into every case (e.g. GS_TUNE_FWD_V1 = 32)
+EXTRA = int(os.environ.get("GS_SAN_TUNING", "0"))   # OR-ed into every case (e.g. GS_TUNE_FWD_WS = 32)
 for (P, V, hw, tuning, depth, sr, sh) in [(3001, 3, (40, 56), 0, True, False, True),
                                           (777, 1, (16, 16), GS_TUNE_FORCE_RADIX_BINNING, False, True, True),
                                           (5000, 2, (33, 70), 0, True, False, False),
                                           (130, 10, (64, 64), 0, False, False, True),
-                                          # round-2 A/B variants: round-1 compositors, merge-sorted strata, two-phase
+                                          # round-2 A/B variants: warp-specialised forward + round-1 backward compositor, merge-sorted strata, two-phase
                                           # preprocess backward, 4-CTA backward compositor
-                                          (2500, 2, (48, 48), GS_TUNE_FWD_V1 | GS_TUNE_BWD_V1 | GS_TUNE_STRATA_MERGE_SORT, True, False, True),
+                                          (2500, 2, (48, 48), GS_TUNE_FWD_WS | GS_TUNE_BWD_V1 | GS_TUNE_STRATA_MERGE_SORT, True, False, True),
                                           (2500, 2, (48, 48), GS_TUNE_PBWD_2PHASE | GS_TUNE_BWD_OCC4, False, True, True)]:
     sc = make_scene(P, V, *hw, seed=P).to(dev)
     vb = make_view_batch(sc.extrinsics, sc.intrinsics, sc.near, sc.far)
