@@ -412,7 +412,8 @@ def main():
 
         for _ in range(3):
             fwd4()                      # exact -> trial -> steady state
-        ms4 = timed(fwd4_counted, steps4, 3)
+        ms4_first = timed(fwd4_counted, steps4, 3)
+        ms4 = timed(fwd4_counted, steps4, 1)     # reported: the second timed loop (the first one is kept as `first_loop_ms`)
         st4 = rasterizer.last_stats(dev)
         # per-rank view of the same loop (its own CUDA events), gathered: who is the slowest and why
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -432,7 +433,7 @@ def main():
         c4 = {"workload": WORKLOADS["c4"][3], "scaling": "strong", "views_total": V4, "views_per_gpu": len(mine4),
               "steps": steps4, "ms_per_step": ms4 / steps4, "views_per_sec_512": V4 * steps4 / (ms4 * 1e-3),
               "gaussians_per_sec": P4 * V4 * steps4 / (ms4 * 1e-3), "tile_instances_rank0": st4["num_rendered"],
-              "speculative": st4["speculative"],
+              "speculative": st4["speculative"], "first_loop_ms_per_step": ms4_first / steps4,
               "per_rank": [{"ms_per_step": float(t[0]), "tile_instances": int(t[1]), "speculative": int(t[2]),
                             "exact_path_calls_in_timed_loop": int(t[3])} for t in allr]}
         del d4, bs4
