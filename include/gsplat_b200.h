@@ -146,7 +146,7 @@ typedef struct GsStats {
     int32_t kernel_launches; /* OUR kernels launched by the last forward (+ backward, if it followed); CUB's scan/sort launches are not counted */
     int32_t max_tile_list;   /* longest (view, tile) list of the last forward */
     int32_t speculative;     /* last forward: 0 exact capacities; 1 speculative capacities (no count/scan/emit passes); 2 the same, binned by depth stratum */
-    int32_t reserved_;
+    int32_t overflow_redos;  /* cumulative over the context's life: speculative forwards whose capacities overflowed and that were redone exactly */
 } GsStats;
 
 typedef struct GsContext GsContext; /* per (device, caller) workspace; not thread-safe, one call at a time */

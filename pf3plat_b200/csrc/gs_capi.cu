@@ -558,6 +558,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
             return GS_OK;
         }
         // overflow: some sub-bucket or tile list outgrew its capacity.  Results are invalid; redo exactly.
+        ctx->stats.overflow_redos++;
         ctx->spec.sub_cap = 0;
         if (strata) {
             if (ctx->spec.strata_state == STRATA_TRIAL && !per_tile && !(cfg->tuning & GS_TUNE_NO_TILE_STRATA)) {
