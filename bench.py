@@ -358,8 +358,9 @@ def main():
             state["k"] += 1
             state["calls"] += 1
 
-        fwd_moving(); fwd_moving(); fwd_moving()                    # exact -> trial -> steady state
-        state.update(calls=0)
+        for _ in range(3 + nvar):                                  # exact -> trial -> steady state, then once through every
+            fwd_moving()                                            # variant: the sticky capacities ratchet up to the largest
+        state.update(calls=0)                                       # (each growth re-allocates ~100 MB of buckets, ~1 ms)
         redos0 = rasterizer.last_stats(dev)["overflow_redos"]
         ms_mov = timed(fwd_moving, args.steps, args.warmup)
         state["overflows"] = rasterizer.last_stats(dev)["overflow_redos"] - redos0
