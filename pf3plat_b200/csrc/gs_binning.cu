@@ -743,11 +743,8 @@ int bin_sort_strata(const DevCfg &c, uint32_t sub_cap, const uint32_t *cursor, c
         const uint32_t nvt = (uint32_t)c.V * (uint32_t)c.ntiles;
         const uint32_t cap_pad = (sub_cap + 31u) & ~31u;
         const size_t smem = (size_t)RS_WARPS * cap_pad * 8;
-        static size_t smem_set = 0;
-        if (smem > smem_set) {
+        if (smem > ((size_t)48 << 10))  // (per device and cheap: no process-wide cache, a process may drive several GPUs)
             GS_CUDA_OK(cudaFuncSetAttribute(k_stratum_rank_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            smem_set = smem;
-        }
         const uint32_t ctas = (nvt * BIN_SUB + RS_WARPS - 1) / RS_WARPS;
         k_stratum_rank_sort<<<ctas, RS_WARPS * 32, smem, st>>>(nvt, sub_cap, cap_pad, cursor, static_cast<const uint64_t *>(bucket),
                                                                point_list, ranges, acc, info, rec2, (uint32_t)c.P, (uint32_t)c.ntiles,
