@@ -48,13 +48,21 @@ def ours_fwd(grad):
 
 
 def timeit(fn, grad):
+    from pf3plat_b200.rasterizer import last_stats
     for _ in range(3):
         fn(grad)
     torch.cuda.synchronize()
+    per = []
     t0 = time.perf_counter()
     for _ in range(steps):
+        t1 = time.perf_counter()
         fn(grad)
+        if os.environ.get("GS_VERBOSE"):
+            torch.cuda.synchronize()
+            per.append((round(1e3 * (time.perf_counter() - t1), 3), last_stats(dev)["speculative"], last_stats(dev)["overflow_redos"]))
     torch.cuda.synchronize()
+    if per:
+        sys.stderr.write(f"{fn.__name__} grad={grad}: {per}\n")
     return 1e3 * (time.perf_counter() - t0) / steps
 
 

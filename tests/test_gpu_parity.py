@@ -162,6 +162,36 @@ def test_batched_backward_sums_views_and_matches_oracle():
     check_grad("batched dL/dcov3D", g6, gc, aff)
 
 
+@pytest.mark.parametrize("d_sh,P", [(1, 1000), (4, 1001), (9, 777), (16, 1300), (16, 129), (25, 1301), (25, 63)])
+def test_sh_coefficient_counts_and_ragged_blocks(d_sh, P):
+    """Every staging path of the SH block, forward and backward, against the oracle: M <= 16 (one bulk TMA copy when the
+    CTA's block is 16-byte aligned, the plain loop for ragged tails and unaligned slices), M = 25 (4-byte cp.async gather
+    of the 16 evaluated coefficients into odd-stride rows; zero bands appended to the gradient), Gaussian counts that are
+    not multiples of the CTA size."""
+    from pf3plat_b200.render import render_views
+    dev = _dev()
+    sc = make_scene(P, 2, 48, 48, seed=40 + d_sh, d_sh=d_sh)
+    d = sc.to(dev)
+    leaves = [t.clone().requires_grad_(True) for t in (d.means[None], d.covariances[None], d.harmonics[None], d.opacities[None])]
+    color = render_views(d.extrinsics, d.intrinsics, d.near, d.far, d.image_shape, d.background, *leaves)
+    target = make_target(2, 48, 48).to(dev)
+    ((color - target) ** 2).mean().backward()
+    gm = np.zeros((P, 3)); gs = np.zeros((P, d_sh, 3))
+    aff = np.zeros(P, bool)
+    for v in range(2):
+        orc = oracle_view(sc, v)
+        check_image(color[v], orc)
+        aff |= affected_of(orc)
+        dL = (2 * (orc.color - target[v].cpu().numpy()) / target.numel()).astype(np.float32)
+        g = orc.backward(dL)
+        gm += g["means3D"]; gs += g["shs"]
+    check_grad(f"d_sh={d_sh} dL/dmeans", leaves[0].grad[0], gm, aff)
+    bands = [b for b in SH_BANDS if b[1].start < d_sh]
+    check_grad(f"d_sh={d_sh} dL/dshs", leaves[2].grad[0].permute(0, 2, 1), gs, aff, bands=bands)
+    if d_sh > 16:
+        assert float(leaves[2].grad[0][..., 16:].abs().max()) == 0.0
+
+
 def test_edge_cases():
     from pf3plat_b200.rasterizer import BatchSettings, rasterize_batch
     dev = _dev()
