@@ -44,13 +44,20 @@ def call():
     _capi.check(L.gs_render_host(ctx, ctypes.byref(cfg), ctypes.byref(gin), ctypes.byref(gout), stream))
 
 
-variants = [int(x) for x in os.environ.get("AB_PIECES", "1,2,4,6,8").split(",")]
+# AB_TUNING: comma-separated full tuning words instead of piece counts (e.g. "0,32768" = images written directly into the
+# pinned output buffer vs copied back by the copy engine)
+if os.environ.get("AB_TUNING"):
+    variants = [int(x) for x in os.environ["AB_TUNING"].split(",")]
+    word = lambda n: n
+else:
+    variants = [int(x) for x in os.environ.get("AB_PIECES", "1,2,4,6,8").split(",")]
+    word = lambda n: n << _capi.GS_TUNE_FEED_PIECES_SHIFT
 for _ in range(5):
     call()
 res = {n: [] for n in variants}
 for rep in range(5):
     for n in variants:
-        cfg.tuning = n << _capi.GS_TUNE_FEED_PIECES_SHIFT
+        cfg.tuning = word(n)
         call()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
