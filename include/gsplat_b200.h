@@ -68,7 +68,7 @@ enum {
     GS_TUNE_PRE_OCC6 = 4096u,         /* preprocess: registers bounded to 80 (6 CTAs/SM) instead of unbounded (96, 5 CTAs/SM) (A/B) */
     GS_TUNE_PBWD_2PHASE = 8192u,      /* preprocess backward: the two-phase kernel (geometry, then one pass per colour channel: 80 registers) instead of the single-pass one (128 registers) (A/B: slower) */
     GS_TUNE_NO_TILE_STRATA = 16384u,  /* stratified binning: never fall back to per-(view, tile) boundaries when the per-view trial overflows (the shape then stays on whole-tile sorts) */
-    GS_TUNE_NO_DIRECT_OUTPUT = 32768u, /* gs_render_host: copy the images back with the copy engine even when the caller's buffers are pinned (default: the compositor writes them directly) (A/B) */
+    GS_TUNE_DIRECT_OUTPUT = 32768u,   /* gs_render_host: the compositor writes the images directly into pinned caller buffers instead of a device-to-host copy afterwards (A/B: 1 % slower) */
     GS_TUNE_FEED_PIECES_SHIFT = 8     /* gs_render_host: bits 8..11 = pieces the SH block is copied in (0 default, 1 = one plain copy) */
 };
 

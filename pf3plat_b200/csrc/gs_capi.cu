@@ -801,9 +801,11 @@ extern "C" int gs_render_host(GsContext *ctx, const GsConfig *cfg, const GsInput
     dout.radii = reinterpret_cast<int32_t *>(base + out_off + align256(px * 12));
     dout.depth = (cfg->flags & GS_FLAG_DEPTH) ? reinterpret_cast<float *>(base + out_off + align256(px * 12) + align256(VP * 4))
                                               : nullptr;
-    // Images go STRAIGHT into the caller's buffers when those are pinned (device-accessible under unified addressing):
-    // the compositor's stores travel over PCIe while it is still running, instead of a device-to-host copy of the whole
-    // image queued behind it (C2: 6.3 MB, 0.12 ms at the very end of the call).  Pageable buffers keep the copy.
+    // Experiment (GS_TUNE_DIRECT_OUTPUT): let the compositor write the images STRAIGHT into the caller's buffers when those
+    // are pinned (device-accessible under unified addressing), instead of a device-to-host copy of the whole image queued
+    // behind it (C2: 6.3 MB, 0.12 ms at the very end of the call).  Measured in-process on C2 (scripts/ab_e2e.py): 3.772 ms
+    // direct vs 3.724 ms with the copy -- 32-byte posted writes over PCIe cost the compositor more than the copy engine's
+    // one burst afterwards.  The copy stays the default.
     auto device_alias = [](void *host) -> void * {
         cudaPointerAttributes at{};
         if (host && cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
@@ -811,8 +813,9 @@ extern "C" int gs_render_host(GsContext *ctx, const GsConfig *cfg, const GsInput
         cudaGetLastError();  // (an unregistered pointer is not an error for us)
         return nullptr;
     };
-    void *color_alias = (cfg->tuning & GS_TUNE_NO_DIRECT_OUTPUT) ? nullptr : device_alias(out->color);
-    void *depth_alias = (cfg->tuning & GS_TUNE_NO_DIRECT_OUTPUT) || !dout.depth ? nullptr : device_alias(out->depth);
+    const bool direct = (cfg->tuning & GS_TUNE_DIRECT_OUTPUT) != 0;
+    void *color_alias = direct ? device_alias(out->color) : nullptr;
+    void *depth_alias = direct && dout.depth ? device_alias(out->depth) : nullptr;
     if (color_alias) dout.color = static_cast<float *>(color_alias);
     if (depth_alias) dout.depth = static_cast<float *>(depth_alias);
     rc = gs_forward(ctx, &dc, &din, &dout, nullptr, stream);

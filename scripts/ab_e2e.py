@@ -44,8 +44,8 @@ def call():
     _capi.check(L.gs_render_host(ctx, ctypes.byref(cfg), ctypes.byref(gin), ctypes.byref(gout), stream))
 
 
-# AB_TUNING: comma-separated full tuning words instead of piece counts (e.g. "0,32768" = images written directly into the
-# pinned output buffer vs copied back by the copy engine)
+# AB_TUNING: comma-separated full tuning words instead of piece counts (e.g. "0,32768" = images copied back by the copy
+# engine vs written directly into the pinned output buffer by the compositor)
 if os.environ.get("AB_TUNING"):
     variants = [int(x) for x in os.environ["AB_TUNING"].split(",")]
     word = lambda n: n

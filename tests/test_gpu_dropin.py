@@ -189,11 +189,11 @@ def test_host_buffer_entry_matches_device_entry(P):
         _capi.check(_capi.lib().gs_render_host(ctx, ctypes.byref(cfg), ctypes.byref(gin), ctypes.byref(gout),
                                                torch.cuda.current_stream(dev).cuda_stream))
         assert torch.equal(color, c2.cpu()) and torch.equal(radii, r2.cpu()) and torch.equal(depth, d2.cpu())
-    # PINNED output buffers: the compositor writes the images straight into them (no device-to-host image copy); with
-    # GS_TUNE_NO_DIRECT_OUTPUT the copy engine path is taken again -- same bytes either way
+    # PINNED output buffers, and the experiment in which the compositor writes the images straight into them
+    # (GS_TUNE_DIRECT_OUTPUT; default: device-to-host copy afterwards) -- same bytes either way
     pc, pr, pd = color.clone().pin_memory(), radii.clone().pin_memory(), depth.clone().pin_memory()
     gpin = _capi.GsOutputs(color=pc.data_ptr(), radii=pr.data_ptr(), depth=pd.data_ptr())
-    for tuning in (0, _capi.GS_TUNE_NO_DIRECT_OUTPUT):
+    for tuning in (0, _capi.GS_TUNE_DIRECT_OUTPUT):
         cfg.tuning = tuning
         pc.zero_(); pr.zero_(); pd.zero_()
         _capi.check(_capi.lib().gs_render_host(ctx, ctypes.byref(cfg), ctypes.byref(gin), ctypes.byref(gpin),
