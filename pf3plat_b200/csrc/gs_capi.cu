@@ -98,6 +98,7 @@ struct GsContext {
     // behind them, so all but the last piece of preprocess hides under the host-to-device transfer
     static constexpr int FEED_MAX = 8;
     int feed_chunks = 0;
+    bool sh_zero_copy = false;         // gs_render_host: in->shs is the device alias of the caller's pinned buffer (preprocess pulls it over PCIe)
     int feed_begin[FEED_MAX + 1] = {};
     cudaEvent_t feed_ev[FEED_MAX] = {};
     GsStats stats{};
@@ -349,7 +350,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     const DevCfg c = make_dev_cfg(cfg);
     const DevInputs di = make_dev_inputs(in);
     const size_t n = (size_t)c.V * c.P;
-    const bool pre_low = (cfg->tuning & GS_TUNE_PRE_OCC6) != 0;
+    const int pre_low = ((cfg->tuning & GS_TUNE_PRE_OCC6) ? 1 : 0) | (((cfg->tuning & GS_TUNE_PRE_SH_RAW16) || ctx->sh_zero_copy) ? 2 : 0);
     for (bool &v : ctx->ev_valid) v = false;
     ctx->stats.kernel_launches = 0;
 
@@ -733,6 +734,23 @@ extern "C" int gs_render_host(GsContext *ctx, const GsConfig *cfg, const GsInput
     GsConfig dc = *cfg;
     GsInputs din{};
     GsOutputs dout{};
+    // device-side address of a PINNED host buffer (unified addressing), or null
+    auto device_alias = [](const void *host) -> void * {
+        cudaPointerAttributes at{};
+        if (host && cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+            return at.devicePointer;
+        cudaGetLastError();  // (an unregistered pointer is not an error for us)
+        return nullptr;
+    };
+    // ZERO-COPY FEED of the SH block (default when the caller's buffer is pinned and M > 16).  The block is most of the
+    // bytes (C2: 150 of 170 MB) and the evaluator reads 192 of every 300-byte row.  Instead of the copy engine moving whole
+    // rows into a device buffer that preprocess then reads, preprocess pulls the 16-byte pieces it wants straight out of
+    // the host buffer while staging them into shared memory (k_preprocess, sh_raw16): no device copy of the block, no
+    // piece events, and the link carries 13 % fewer bytes (64-byte granularity: scripts/probes/pcie_pull_probe.cu).
+    void *sh_alias = nullptr;
+    if (in->shs && cfg->M > 16 && !(cfg->tuning & GS_TUNE_NO_ZERO_COPY) &&
+        (reinterpret_cast<uintptr_t>(in->shs) & 15u) == 0 && (cfg->S == 1 || ((size_t)cfg->P * cfg->M * 12) % 16 == 0))
+        sh_alias = device_alias(in->shs);
     Item items[] = {
         {cfg->viewmatrix, V * 64, (const void **)&dc.viewmatrix},
         {cfg->projmatrix, V * 64, (const void **)&dc.projmatrix},
@@ -742,7 +760,7 @@ extern "C" int gs_render_host(GsContext *ctx, const GsConfig *cfg, const GsInput
         {cfg->view_scale, cfg->view_scale ? V * 4 : 0, (const void **)&dc.view_scale},
         {in->means3D, SP * 12, (const void **)&din.means3D},
         {in->opacities, SP * 4, (const void **)&din.opacities},
-        {in->shs, in->shs ? SP * cfg->M * 12 : 0, (const void **)&din.shs},
+        {in->shs, (in->shs && !sh_alias) ? SP * cfg->M * 12 : 0, (const void **)&din.shs},
         {in->colors_precomp, in->colors_precomp ? VP * 12 : 0, (const void **)&din.colors_precomp},
         {in->scales, in->scales ? SP * 12 : 0, (const void **)&din.scales},
         {in->rotations, in->rotations ? SP * 16 : 0, (const void **)&din.rotations},
@@ -763,7 +781,7 @@ extern "C" int gs_render_host(GsContext *ctx, const GsConfig *cfg, const GsInput
     // stream, each marked with an event, and gs_forward runs preprocess piece by piece behind them.
     const size_t sh_row = (size_t)cfg->M * 12;
     int pieces = 0;
-    if (in->shs && cfg->S == 1 && (size_t)cfg->P * sh_row >= ((size_t)16 << 20)) {
+    if (in->shs && !sh_alias && cfg->S == 1 && (size_t)cfg->P * sh_row >= ((size_t)16 << 20)) {
         // measured on C2 inside one process (scripts/ab_e2e.py): 1 plain copy 3.965 ms, 2 pieces 3.863, 4: 3.820, 6: 3.799
         const int req = (int)((cfg->tuning >> GS_TUNE_FEED_PIECES_SHIFT) & 0xFu);
         pieces = req == 0 ? 6 : (req == 1 ? 0 : (req > GsContext::FEED_MAX ? GsContext::FEED_MAX : req));
@@ -780,6 +798,7 @@ extern "C" int gs_render_host(GsContext *ctx, const GsConfig *cfg, const GsInput
         }
         off += align256(it.bytes);
     }
+    if (sh_alias) din.shs = static_cast<const float *>(sh_alias);
     if (pieces) {
         const int step = ((cfg->P + pieces - 1) / pieces + 511) / 512 * 512;  // whole CTAs, 16-byte aligned rows
         int k = 0;
@@ -806,19 +825,14 @@ extern "C" int gs_render_host(GsContext *ctx, const GsConfig *cfg, const GsInput
     // behind it (C2: 6.3 MB, 0.12 ms at the very end of the call).  Measured in-process on C2 (scripts/ab_e2e.py): 3.772 ms
     // direct vs 3.724 ms with the copy -- 32-byte posted writes over PCIe cost the compositor more than the copy engine's
     // one burst afterwards.  The copy stays the default.
-    auto device_alias = [](void *host) -> void * {
-        cudaPointerAttributes at{};
-        if (host && cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
-            return at.devicePointer;
-        cudaGetLastError();  // (an unregistered pointer is not an error for us)
-        return nullptr;
-    };
     const bool direct = (cfg->tuning & GS_TUNE_DIRECT_OUTPUT) != 0;
     void *color_alias = direct ? device_alias(out->color) : nullptr;
     void *depth_alias = direct && dout.depth ? device_alias(out->depth) : nullptr;
     if (color_alias) dout.color = static_cast<float *>(color_alias);
     if (depth_alias) dout.depth = static_cast<float *>(depth_alias);
+    ctx->sh_zero_copy = sh_alias != nullptr;
     rc = gs_forward(ctx, &dc, &din, &dout, nullptr, stream);
+    ctx->sh_zero_copy = false;
     ctx->host_radii_dst = nullptr;
     ctx->feed_chunks = 0;
     if (rc != GS_OK) return rc;

@@ -72,7 +72,8 @@ struct PreEmit {
 
 int launch_preprocess(const DevCfg &c, const DevInputs &in, float4 *rec0, float4 *rec1, float4 *rec2, uint8_t *meta,
                       int32_t *radii, ushort4 *rects, const PreEmit &emit, cudaStream_t st, int g_begin = 0,
-                      int g_end = -1 /* = P */, bool more_ctas = false /* 80 registers, 6 CTAs/SM (GS_TUNE_PRE_OCC6) */);
+                      int g_end = -1 /* = P */,
+                      int variant = 0 /* bit 0: 80 registers, 6 CTAs/SM (GS_TUNE_PRE_OCC6); bit 1: M > 16 rows staged as 16-byte pieces at their own stride (zero-copy feed, GS_TUNE_PRE_SH_RAW16) */);
 int launch_mark_visible(const DevCfg &c, const float *means3D, uint8_t *present, cudaStream_t st);
 
 // binning (gs_binning.cu)

@@ -133,7 +133,7 @@ template <bool HAS_SH, int MINB>
 __global__ void __launch_bounds__(PRE_THREADS, MINB)
 k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, float4 *__restrict__ rec1,
              float4 *__restrict__ rec2, uint8_t *__restrict__ meta, int32_t *__restrict__ radii,
-             ushort4 *__restrict__ rects, const PreEmit emit, const int g_begin, const int g_end) {
+             ushort4 *__restrict__ rects, const PreEmit emit, const int g_begin, const int g_end, const int sh_raw16) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PreSmem *sm = reinterpret_cast<PreSmem *>(smem_raw);
     float *sh_s = reinterpret_cast<float *>(smem_raw + PRE_SMEM_HDR);
@@ -147,17 +147,22 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
     const size_t sg = (size_t)scene * c.P + i;  // scene-level index
 
     // ---- stage this CTA's SH block ----
-    // Only the bands the evaluator can touch are staged: MS = min(M, 16) coefficients per Gaussian (PF3plat hands over
-    // M = 25 of which 16..24 are never read): 192 instead of 300 bytes of shared memory per thread, which is what lets
-    // eight CTAs share an SM.  M <= 16: the block is contiguous and arrives by ONE 1-D bulk TMA copy (cp.async.bulk,
-    // SASS UBLKCP) completing on an mbarrier.  M > 16: the wanted 192 bytes of every 12*M-byte row are copied with
-    // coalesced loads (rows are not 16-byte aligned -- 300 = 18 * 16 + 12 -- so neither a bulk copy per row nor a 2-D
-    // tensor map is possible).
+    // Only the bands the evaluator can touch are wanted: MS = min(M, 16) coefficients per Gaussian (PF3plat hands over
+    // M = 25 of which 16..24 are never read).
+    //  * M <= 16: the block is contiguous and arrives by ONE 1-D bulk TMA copy (cp.async.bulk, SASS UBLKCP) completing on
+    //    an mbarrier.
+    //  * M > 16 (default): the wanted 192 bytes of every row are gathered with 4-byte cp.async into rows compacted to an
+    //    ODD stride (49 floats): with 48, thread t's row starts at bank 16 t mod 32 and all 32 lanes of a warp hit two
+    //    banks (measured: 90 M bank conflicts, preprocess 0.24 -> 0.47 ms).  Rows are only 4-byte aligned (300 = 18 * 16 +
+    //    12), so neither a bulk copy per row nor a 2-D tensor map is possible.
+    //  * M > 16, sh_raw16 (gs_render_host's ZERO-COPY feed; GS_TUNE_PRE_SH_RAW16 for the A/B): rows keep their own stride of
+    //    3 M floats in shared memory and only the 16-byte pieces that hold a wanted coefficient are copied (16-byte
+    //    cp.async, SASS LDGSTS.128).  Built for a source in PINNED HOST memory, which is pulled over PCIe at the rate of
+    //    16-byte loads (scripts/probes/pcie_pull_probe.cu: 4-byte loads 2.96 ms, 16-byte loads 2.53 ms, the copy engine
+    //    2.70 ms for the whole rows).  On device-resident SH it loses to the compacting gather (C2: 0.246 vs 0.220 ms --
+    //    38 instead of 25 KB of shared memory per CTA leave the L1 28 KB at five CTAs per SM).
     const int MS = c.M < 16 ? c.M : 16;
-    // floats per staged row.  The compacted rows are padded to an ODD stride (49): with 48, thread t's row starts at bank
-    // 16 t mod 32 and all 32 lanes of a warp hit two banks (measured: 90 M bank conflicts, preprocess 0.24 -> 0.47 ms).
-    // Bulk-copied blocks keep the input's own stride (3 M).
-    const int RS = c.M == MS ? c.M * 3 : 49;
+    const int RS = (c.M == MS || sh_raw16) ? c.M * 3 : 49;   // floats per staged row (3 M = 75 for PF3plat: 11 t mod 32, conflict-free)
     bool bulk = false;
     if (HAS_SH) {
         const float *src = in.shs + ((size_t)scene * c.P + g0) * c.M * 3;
@@ -174,6 +179,17 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
             } else {  // unaligned slice or ragged tail: plain coalesced copy
                 for (uint32_t k = tid; k < (uint32_t)n * c.M * 3u; k += PRE_THREADS) sh_s[k] = src[k];
             }
+        } else if (sh_raw16) {
+            const uint32_t row_f = (uint32_t)c.M * 3u, want_f = (uint32_t)MS * 3u, nfl = (uint32_t)n * row_f, nq = nfl >> 2;
+            const float4 *src4 = reinterpret_cast<const float4 *>(src);
+            for (uint32_t q = tid; q < nq; q += PRE_THREADS) {
+                const uint32_t f0 = q << 2, r = f0 / row_f, c0 = f0 - r * row_f;
+                // floats [c0, c0 + 4) of row r (running over into the next row's first coefficients when c0 + 3 >= row_f)
+                if (c0 < want_f || c0 + 3u >= row_f) cp_async16(sh_s + f0, src4 + q);
+            }
+            for (uint32_t f = (nq << 2) + tid; f < nfl; f += PRE_THREADS)   // ragged end of the block (n * row_f % 4 floats)
+                if (f % row_f < want_f) cp_async4(sh_s + f, src + f);
+            cp_async_commit();
         } else {
             // asynchronous 4-byte copies (cp.async, SASS LDGSTS): all 48 per thread are in flight together while the
             // scalar inputs load -- a plain load/store loop here cost 0.25 ms on C2 (serialised latencies)
@@ -326,14 +342,23 @@ __global__ void k_mark_visible(const DevCfg c, const float *__restrict__ means3D
 
 int launch_preprocess(const DevCfg &c, const DevInputs &in, float4 *rec0, float4 *rec1, float4 *rec2, uint8_t *meta,
                       int32_t *radii, ushort4 *rects, const PreEmit &emit, cudaStream_t st, int g_begin, int g_end,
-                      bool more_ctas) {
+                      int variant) {
     if (g_end < 0) g_end = c.P;
     if (g_end <= g_begin) return GS_OK;
+    const bool more_ctas = (variant & 1) != 0;
     dim3 grid((g_end - g_begin + PRE_THREADS - 1) / PRE_THREADS, c.S);
-    const size_t smem = PRE_SMEM_HDR + (in.shs ? (size_t)PRE_THREADS * (c.M <= 16 ? c.M * 3 : 49) * 4 : 0);
+    // M > 16, on request: 16-byte pieces at the rows' own stride -- if every CTA's block starts 16-byte aligned (CTAs cover
+    // 128 rows = 1536 M bytes, so the first one decides -- per scene); else the compacting 4-byte gather
+    int sh_raw16 = 0;
+    if (in.shs && c.M > 16 && (variant & 2)) {
+        const uintptr_t first = reinterpret_cast<uintptr_t>(in.shs) + (size_t)g_begin * c.M * 12;
+        sh_raw16 = (first & 15u) == 0 && (c.S == 1 || ((size_t)c.P * c.M * 12) % 16 == 0);
+    }
+    const size_t smem = PRE_SMEM_HDR + (in.shs ? (size_t)PRE_THREADS * ((c.M <= 16 || sh_raw16) ? c.M * 3 : 49) * 4 : 0);
+    if (smem > (size_t)227 * 1024) return gs_set_error(GS_ERR_INVALID, "too many SH coefficients per Gaussian for the staging buffer");
     auto launch = [&](auto kern) -> int {
         GS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, PRE_THREADS, smem, st>>>(c, in, rec0, rec1, rec2, meta, radii, rects, emit, g_begin, g_end);
+        kern<<<grid, PRE_THREADS, smem, st>>>(c, in, rec0, rec1, rec2, meta, radii, rects, emit, g_begin, g_end, sh_raw16);
         return GS_OK;
     };
     int rc;
