@@ -71,6 +71,7 @@ enum {
     GS_TUNE_DIRECT_OUTPUT = 32768u,   /* gs_render_host: the compositor writes the images directly into pinned caller buffers instead of a device-to-host copy afterwards (A/B: 1 % slower) */
     GS_TUNE_PRE_SH_RAW16 = 65536u,    /* preprocess, M > 16, device-resident SH: stage 16-byte pieces at the rows' own stride (what the zero-copy feed of gs_render_host uses) instead of gathering the 16 evaluated coefficients with 4-byte copies into compacted rows (A/B: 0.246 vs 0.220 ms on C2) */
     GS_TUNE_NO_ZERO_COPY = 131072u,   /* gs_render_host: always upload the SH block with the copy engine (in pieces) even when the caller's buffer is pinned and preprocess could pull it over PCIe itself (A/B) */
+    GS_TUNE_NO_SPLIT_COLOUR = 262144u, /* gs_render_host, zero-copy feed: one fused preprocess pulling the SH block instead of geometry + tile sort on the launch stream with k_sh_colour pulling the block on a second stream (A/B) */
     GS_TUNE_FEED_PIECES_SHIFT = 8     /* gs_render_host: bits 8..11 = pieces the SH block is copied in (0 default, 1 = one plain copy) */
 };
 
@@ -291,7 +292,8 @@ enum { GS_STAGE_PREPROCESS = 0,      /* k_preprocess (incl. tile counting) */
        GS_STAGE_COMPOSITE = 4,       /* k_composite_fwd */
        GS_STAGE_COMPOSITE_BWD = 5,   /* accumulator memset + k_composite_bwd */
        GS_STAGE_PREPROCESS_BWD = 6,  /* k_preprocess_bwd */
-       GS_NUM_STAGES = 7 };
+       GS_STAGE_SH_COLOUR = 7,       /* k_sh_colour on its own stream (gs_render_host's split pipeline; overlaps stages 0-3) */
+       GS_NUM_STAGES = 8 };
 GS_API int gs_set_profiling(GsContext *ctx, int enabled);
 GS_API int gs_get_stage_ms(GsContext *ctx, float *ms /* [GS_NUM_STAGES] */);
 

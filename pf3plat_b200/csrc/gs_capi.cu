@@ -88,6 +88,10 @@ struct GsContext {
     GrowBuf strata;        // [V][BIN_SUB] stratum boundaries + histogram scratch
     cudaEvent_t ev_pre = nullptr;   // "preprocess done" (speculative path: lets the radii copy start early)
     cudaEvent_t ev_info = nullptr;  // "binning verdict copied to the host"
+    // gs_render_host's split pipeline: k_sh_colour pulls the SH block out of the caller's pinned buffer on aux_stream while
+    // geometry, binning and the tile sort run on the launch stream; the compositor waits for ev_colour
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_alloc = nullptr, ev_colour = nullptr;
     // gs_render_host: radii are final once the forward's mid-way sync has passed, so their copy to the host
     // overlaps binning + compositing on a side stream
     cudaStream_t copy_stream = nullptr;
@@ -263,6 +267,9 @@ extern "C" void gs_context_destroy(GsContext *ctx) {
     ctx->host_stage.release();
     ctx->strata.release();
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->ev_alloc) cudaEventDestroy(ctx->ev_alloc);
+    if (ctx->ev_colour) cudaEventDestroy(ctx->ev_colour);
     for (cudaEvent_t ev : ctx->feed_ev)
         if (ev) cudaEventDestroy(ev);
     if (ctx->ev_pre) cudaEventDestroy(ctx->ev_pre);
@@ -350,7 +357,10 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     const DevCfg c = make_dev_cfg(cfg);
     const DevInputs di = make_dev_inputs(in);
     const size_t n = (size_t)c.V * c.P;
-    const int pre_low = ((cfg->tuning & GS_TUNE_PRE_OCC6) ? 1 : 0) | (((cfg->tuning & GS_TUNE_PRE_SH_RAW16) || ctx->sh_zero_copy) ? 2 : 0);
+    // gs_render_host with a pinned SH block: geometry-only preprocess here, colours by k_sh_colour on a second stream
+    const bool split_colour = ctx->sh_zero_copy && !(cfg->tuning & GS_TUNE_NO_SPLIT_COLOUR) && n > 0 && sh_colour_supported(c, di);
+    const int pre_low = ((cfg->tuning & GS_TUNE_PRE_OCC6) ? 1 : 0) | (((cfg->tuning & GS_TUNE_PRE_SH_RAW16) || ctx->sh_zero_copy) ? 2 : 0) |
+                        (split_colour ? 4 : 0);
     for (bool &v : ctx->ev_valid) v = false;
     ctx->stats.kernel_launches = 0;
 
@@ -391,9 +401,40 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
         s->base = block;
         s->bytes = bytes;
     }
+    bool colour_pending = false;   // k_sh_colour is (or may still be) writing into s->rec1 / s->rec2 on the aux stream
     auto fail = [&](int code) {
+        if (colour_pending) cudaStreamWaitEvent(st, ctx->ev_colour, 0);   // the free below is ordered on `st`
         gs_saved_free(ctx, s, stream);
         return code;
+    };
+    if (split_colour) {
+        cudaError_t e = cudaSuccess;
+        if (!ctx->aux_stream) e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess && !ctx->ev_alloc) e = cudaEventCreateWithFlags(&ctx->ev_alloc, cudaEventDisableTiming);
+        if (e == cudaSuccess && !ctx->ev_colour) e = cudaEventCreateWithFlags(&ctx->ev_colour, cudaEventDisableTiming);
+        // everything enqueued on `st` so far -- the caller's uploads of means and cameras, the allocation of the records --
+        // precedes the colour kernel
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_alloc, st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_alloc, 0);
+        if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "split colour pipeline setup", __FILE__, __LINE__));
+        {
+            StageTimer t(ctx, GS_STAGE_SH_COLOUR, ctx->aux_stream);
+            rc = launch_sh_colour(c, di, s->rec1, s->rec2, nullptr, ctx->aux_stream);
+        }
+        if (rc != GS_OK) return fail(rc);
+        colour_pending = true;
+        e = cudaEventRecord(ctx->ev_colour, ctx->aux_stream);
+        if (e != cudaSuccess) {
+            cudaStreamSynchronize(ctx->aux_stream);
+            colour_pending = false;
+            return fail(gs_set_cuda_error(e, "cudaEventRecord(colour)", __FILE__, __LINE__));
+        }
+    }
+    // the compositor needs the colour words: called right before each of its launches
+    auto join_colour = [&]() -> cudaError_t {
+        if (!colour_pending) return cudaSuccess;
+        colour_pending = false;   // from here on `st` itself is ordered behind the colour kernel
+        return cudaStreamWaitEvent(st, ctx->ev_colour, 0);
     };
 
     // ---- speculative-capacity forward: no count/scan passes and no mid-pipeline bubble ----
@@ -509,6 +550,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
             }
             if (rc != GS_OK) return fail(rc);
         }
+        if ((e = join_colour()) != cudaSuccess) return fail(gs_set_cuda_error(e, "cudaStreamWaitEvent(colour)", __FILE__, __LINE__));
         {
             StageTimer t(ctx, GS_STAGE_COMPOSITE, st);
             rc = launch_composite_fwd(c, *s, out->color, out->depth, st, (cfg->tuning & GS_TUNE_FWD_WS) ? 2 : 0);
@@ -547,7 +589,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
             s->flags = c.flags;
             s->has_sh = in->shs != nullptr;
             s->has_scales = in->scales != nullptr;
-            ctx->stats.kernel_launches = (strata ? 3 : 4) + (fused_emit ? 0 : 1);  // k_preprocess, [k_emit_buckets], [k_spec_check,] tile sort, k_composite_fwd
+            ctx->stats.kernel_launches = (strata ? 3 : 4) + (fused_emit ? 0 : 1) + (split_colour ? 1 : 0);  // k_preprocess, [k_sh_colour,] [k_emit_buckets], [k_spec_check,] tile sort, k_composite_fwd
             ctx->stats.max_tile_list = (int32_t)ctx->h_word[1];
             ctx->stats.num_rendered = D;
             ctx->stats.num_visible = -1;
@@ -637,6 +679,10 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     ctx->stats.kernel_launches += 1 + (D > 0 ? 1 : 0) + 1;  // scan, emit, tile sort (fallback: 3 + CUB's)
     ctx->stats.max_tile_list = (int32_t)max_count;
 
+    {
+        cudaError_t e = join_colour();
+        if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "cudaStreamWaitEvent(colour)", __FILE__, __LINE__));
+    }
     {
         StageTimer t(ctx, GS_STAGE_COMPOSITE, st);
         rc = launch_composite_fwd(c, *s, out->color, out->depth, st, (cfg->tuning & GS_TUNE_FWD_WS) ? 2 : 0);

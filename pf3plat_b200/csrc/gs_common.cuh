@@ -73,7 +73,10 @@ struct PreEmit {
 int launch_preprocess(const DevCfg &c, const DevInputs &in, float4 *rec0, float4 *rec1, float4 *rec2, uint8_t *meta,
                       int32_t *radii, ushort4 *rects, const PreEmit &emit, cudaStream_t st, int g_begin = 0,
                       int g_end = -1 /* = P */,
-                      int variant = 0 /* bit 0: 80 registers, 6 CTAs/SM (GS_TUNE_PRE_OCC6); bit 1: M > 16 rows staged as 16-byte pieces at their own stride (zero-copy feed, GS_TUNE_PRE_SH_RAW16) */);
+                      int variant = 0 /* bit 0: 80 registers, 6 CTAs/SM (GS_TUNE_PRE_OCC6); bit 1: M > 16 rows staged as 16-byte pieces at their own stride (zero-copy feed, GS_TUNE_PRE_SH_RAW16); bit 2: geometry only, colour words left to k_sh_colour */);
+// the colour words (rec1.zw, rec2.x) of every (view, Gaussian) from the SH block -- gs_render_host's split pipeline
+bool sh_colour_supported(const DevCfg &c, const DevInputs &in);
+int launch_sh_colour(const DevCfg &c, const DevInputs &in, float4 *rec1, float4 *rec2, uint8_t *clamp_out /* [V*P] or NULL */, cudaStream_t st);
 int launch_mark_visible(const DevCfg &c, const float *means3D, uint8_t *present, cudaStream_t st);
 
 // binning (gs_binning.cu)

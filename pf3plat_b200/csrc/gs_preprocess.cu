@@ -23,34 +23,70 @@ struct PreSmem {
 };
 constexpr int PRE_SMEM_HDR = (sizeof(PreSmem) + 127) / 128 * 128;
 
+// SH colour of one Gaussian seen from direction `dir` (unit vector), bands 0..deg (Appendix A "SH -> RGB": upstream's
+// left-to-right sum, +0.5, clamp at 0 with the clamp recorded per channel).  Every operation is an explicit
+// round-to-nearest intrinsic -- no contraction or re-association left to the compiler -- because TWO kernels inline this
+// function (k_preprocess and k_sh_colour, the split pipeline of gs_render_host) and must produce the same bits.
 __device__ __forceinline__ float3 eval_sh(int deg, const float *sh /* [M][3] for this Gaussian */, float3 dir,
                                           uint32_t &clamped) {
     const float x = dir.x, y = dir.y, z = dir.z;
-    float r[3];
+    float v[3];
+    // band by band (basis values of one band live at a time), every channel's sum in upstream's left-to-right order
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-        float v = GS_SH_C0 * sh[0 * 3 + c];
-        if (deg > 0) {
-            v = v - GS_SH_C1 * y * sh[1 * 3 + c] + GS_SH_C1 * z * sh[2 * 3 + c] - GS_SH_C1 * x * sh[3 * 3 + c];
-            if (deg > 1) {
-                const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-                v = v + GS_SH_C2_0 * xy * sh[4 * 3 + c] + GS_SH_C2_1 * yz * sh[5 * 3 + c] +
-                    GS_SH_C2_2 * (2.0f * zz - xx - yy) * sh[6 * 3 + c] + GS_SH_C2_3 * xz * sh[7 * 3 + c] +
-                    GS_SH_C2_4 * (xx - yy) * sh[8 * 3 + c];
-                if (deg > 2) {
-                    v = v + GS_SH_C3_0 * y * (3.0f * xx - yy) * sh[9 * 3 + c] + GS_SH_C3_1 * xy * z * sh[10 * 3 + c] +
-                        GS_SH_C3_2 * y * (4.0f * zz - xx - yy) * sh[11 * 3 + c] +
-                        GS_SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[12 * 3 + c] +
-                        GS_SH_C3_4 * x * (4.0f * zz - xx - yy) * sh[13 * 3 + c] +
-                        GS_SH_C3_5 * z * (xx - yy) * sh[14 * 3 + c] + GS_SH_C3_6 * x * (xx - 3.0f * yy) * sh[15 * 3 + c];
+    for (int c = 0; c < 3; c++) v[c] = __fmul_rn(GS_SH_C0, sh[c]);
+    if (deg > 0) {   // (uniform branches: the degree is a launch constant)
+        const float b1 = __fmul_rn(-GS_SH_C1, y), b2 = __fmul_rn(GS_SH_C1, z), b3 = __fmul_rn(-GS_SH_C1, x);
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+            v[c] = __fmaf_rn(b3, sh[3 * 3 + c], __fmaf_rn(b2, sh[2 * 3 + c], __fmaf_rn(b1, sh[1 * 3 + c], v[c])));
+        if (deg > 1) {
+            const float xx = __fmul_rn(x, x), yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+            const float xy = __fmul_rn(x, y), yz = __fmul_rn(y, z), xz = __fmul_rn(x, z);
+            {
+                const float b4 = __fmul_rn(GS_SH_C2_0, xy), b5 = __fmul_rn(GS_SH_C2_1, yz);
+                const float b6 = __fmul_rn(GS_SH_C2_2, __fsub_rn(__fsub_rn(__fmul_rn(2.0f, zz), xx), yy));
+                const float b7 = __fmul_rn(GS_SH_C2_3, xz), b8 = __fmul_rn(GS_SH_C2_4, __fsub_rn(xx, yy));
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    float t = __fmaf_rn(b5, sh[5 * 3 + c], __fmaf_rn(b4, sh[4 * 3 + c], v[c]));
+                    t = __fmaf_rn(b7, sh[7 * 3 + c], __fmaf_rn(b6, sh[6 * 3 + c], t));
+                    v[c] = __fmaf_rn(b8, sh[8 * 3 + c], t);
+                }
+            }
+            if (deg > 2) {
+                const float zz4 = __fsub_rn(__fsub_rn(__fmul_rn(4.0f, zz), xx), yy);
+                const float b9 = __fmul_rn(__fmul_rn(GS_SH_C3_0, y), __fsub_rn(__fmul_rn(3.0f, xx), yy));
+                const float b10 = __fmul_rn(__fmul_rn(GS_SH_C3_1, xy), z);
+                const float b11 = __fmul_rn(__fmul_rn(GS_SH_C3_2, y), zz4);
+                const float b12 = __fmul_rn(__fmul_rn(GS_SH_C3_3, z), __fsub_rn(__fsub_rn(__fmul_rn(2.0f, zz), __fmul_rn(3.0f, xx)), __fmul_rn(3.0f, yy)));
+                const float b13 = __fmul_rn(__fmul_rn(GS_SH_C3_4, x), zz4);
+                const float b14 = __fmul_rn(__fmul_rn(GS_SH_C3_5, z), __fsub_rn(xx, yy));
+                const float b15 = __fmul_rn(__fmul_rn(GS_SH_C3_6, x), __fsub_rn(xx, __fmul_rn(3.0f, yy)));
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    float t = __fmaf_rn(b10, sh[10 * 3 + c], __fmaf_rn(b9, sh[9 * 3 + c], v[c]));
+                    t = __fmaf_rn(b12, sh[12 * 3 + c], __fmaf_rn(b11, sh[11 * 3 + c], t));
+                    t = __fmaf_rn(b14, sh[14 * 3 + c], __fmaf_rn(b13, sh[13 * 3 + c], t));
+                    v[c] = __fmaf_rn(b15, sh[15 * 3 + c], t);
                 }
             }
         }
-        v += 0.5f;
-        if (v < 0.0f) clamped |= (1u << c);
-        r[c] = fmaxf(v, 0.0f);
+    }
+    float r[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float w = __fadd_rn(v[c], 0.5f);
+        if (w < 0.0f) clamped |= (1u << c);
+        r[c] = fmaxf(w, 0.0f);
     }
     return make_float3(r[0], r[1], r[2]);
+}
+
+// unit vector from the camera to the (scaled) mean; pinned like eval_sh
+__device__ __forceinline__ float3 sh_view_dir(float3 m, const float *campos) {
+    const float dx = __fsub_rn(m.x, campos[0]), dy = __fsub_rn(m.y, campos[1]), dz = __fsub_rn(m.z, campos[2]);
+    const float inv = __frcp_rn(__fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)))));
+    return make_float3(__fmul_rn(dx, inv), __fmul_rn(dy, inv), __fmul_rn(dz, inv));
 }
 
 // Everything preprocess derives for one (view, Gaussian).
@@ -61,9 +97,9 @@ struct Splat {
     ushort4 rect;
 };
 
-// Appendix A "Preprocess" for one Gaussian in one view.  `sh` points at this Gaussian's [M][3] block in shared
-// memory (HAS_SH) ; `rgb_in` is its precomputed colour otherwise.
-template <bool HAS_SH>
+// Appendix A "Preprocess" for one Gaussian in one view.  COLOUR = 2: `sh` points at this Gaussian's [M][3] block in
+// shared memory; 1: `rgb_in` is its precomputed colour; 0: geometry only (the colour words are written by k_sh_colour).
+template <int COLOUR>
 __device__ __forceinline__ void project_splat(const DevCfg &c, const ViewCam &cam, float3 mean, const float *c6,
                                               float opac, const float *sh, const float *rgb_in, Splat &out) {
     out.radius = 0;
@@ -101,14 +137,9 @@ __device__ __forceinline__ void project_splat(const DevCfg &c, const ViewCam &ca
     out.radius = (int32_t)rad;
     out.meta = GS_META_VISIBLE;
     float3 rgb;
-    if (HAS_SH) {
-        float3 d = make_float3(m.x - cam.campos[0], m.y - cam.campos[1], m.z - cam.campos[2]);
-        const float inv = 1.0f / sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
-        d.x *= inv; d.y *= inv; d.z *= inv;
-        rgb = eval_sh(c.deg, sh, d, out.meta);
-    } else {
-        rgb = make_float3(rgb_in[0], rgb_in[1], rgb_in[2]);
-    }
+    if (COLOUR == 2) rgb = eval_sh(c.deg, sh, sh_view_dir(m, cam.campos), out.meta);
+    else if (COLOUR == 1) rgb = make_float3(rgb_in[0], rgb_in[1], rgb_in[2]);
+    else rgb = make_float3(0.f, 0.f, 0.f);   // COLOUR == 0: k_sh_colour fills the three colour words of the record
     // Tight binning.  A pixel can only receive this Gaussian if alpha = o*G >= 1/255, i.e. log2 G >= -log2(255 o).
     // The candidate tiles are upstream's 3-sigma square; k_preprocess / k_emit_buckets keep a candidate only if the
     // alpha >= 1/255 ellipse really reaches it (gs_box_reaches, exact).  Tiles dropped this way cannot change any
@@ -129,7 +160,7 @@ __device__ __forceinline__ void project_splat(const DevCfg &c, const ViewCam &ca
 // MINB: resident CTAs per SM the register allocation is bounded for.  Unbounded the kernel takes 96 registers (5 CTAs/SM,
 // 28 % occupancy; ncu: issue slots 50 % busy, latency-bound).  Measured on C2 with the 16-coefficient staging: 96
 // registers 0.222 ms; bounded to 64 (8 CTAs/SM, 44 % occupancy, 116 bytes of spills = +15 % instructions) 0.275 ms.
-template <bool HAS_SH, int MINB>
+template <int COLOUR, int MINB>
 __global__ void __launch_bounds__(PRE_THREADS, MINB)
 k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, float4 *__restrict__ rec1,
              float4 *__restrict__ rec2, uint8_t *__restrict__ meta, int32_t *__restrict__ radii,
@@ -163,6 +194,7 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
     //    38 instead of 25 KB of shared memory per CTA leave the L1 28 KB at five CTAs per SM).
     const int MS = c.M < 16 ? c.M : 16;
     const int RS = (c.M == MS || sh_raw16) ? c.M * 3 : 49;   // floats per staged row (3 M = 75 for PF3plat: 11 t mod 32, conflict-free)
+    constexpr bool HAS_SH = COLOUR == 2;
     bool bulk = false;
     if (HAS_SH) {
         const float *src = in.shs + ((size_t)scene * c.P + g0) * c.M * 3;
@@ -255,12 +287,18 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
             const int v = scene * c.VPS + v0 + vi;
             const size_t o = (size_t)v * c.P + i;
             Splat sp;
-            project_splat<HAS_SH>(c, sm->cams[vi], mean, c6, opac, sh_s + (size_t)tid * RS,
-                                  HAS_SH ? nullptr : in.colors_precomp + o * 3, sp);
+            project_splat<COLOUR>(c, sm->cams[vi], mean, c6, opac, sh_s + (size_t)tid * RS,
+                                  COLOUR == 1 ? in.colors_precomp + o * 3 : nullptr, sp);
             if (sp.radius > 0) {
                 rec0[o] = sp.r0;
-                rec1[o] = sp.r1;
-                rec2[o] = sp.r2;
+                if (COLOUR != 0) {
+                    rec1[o] = sp.r1;
+                    rec2[o] = sp.r2;
+                } else {   // the colour words (rec1.zw, rec2.x) belong to k_sh_colour, which may be running right now
+                    *reinterpret_cast<float2 *>(&rec1[o]) = make_float2(sp.r1.x, sp.r1.y);
+                    reinterpret_cast<float *>(&rec2[o])[1] = sp.r2.y;
+                    reinterpret_cast<float2 *>(&rec2[o])[1] = make_float2(sp.r2.z, sp.r2.w);
+                }
             }
             radii[o] = sp.radius;
             rects[o] = sp.rect;
@@ -325,6 +363,87 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
     flush_pending();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// k_sh_colour: the colour words of the splat records, computed apart from the geometry (gs_render_host's split pipeline)
+// ---------------------------------------------------------------------------------------------------------
+// With host buffers the SH block is 88 % of the bytes that cross PCIe, and geometry + binning + the tile sort need none
+// of it.  gs_render_host therefore runs k_preprocess in geometry-only mode (COLOUR = 0) followed by the tile sort on the
+// launch stream, while THIS kernel, on a second stream, pulls the SH rows straight out of the caller's pinned buffer
+// (16-byte pieces at the rows' own stride, as k_preprocess's sh_raw16 mode) and writes rec1.zw / rec2.x; the compositor
+// waits for both.  Link-bound by design: a persistent grid of two CTAs per SM with a bounded number of host reads in
+// flight each (see launch_sh_colour) leaves the rest of every SM to the geometry kernel and the sort, which run underneath.
+// Same eval_sh / sh_view_dir as k_preprocess (pinned arithmetic): the split pipeline's images are bit-identical.
+constexpr int SHC_THREADS = 128;
+constexpr int SHC_VIEWS = 64;   // cameras staged at a time
+
+__global__ void __launch_bounds__(SHC_THREADS, 2)
+k_sh_colour(const DevCfg c, const float *__restrict__ means3D, const float *__restrict__ shs, float4 *__restrict__ rec1,
+            float4 *__restrict__ rec2, uint8_t *__restrict__ clamp_out /* [V*P] or NULL */, const int blocks_per_scene,
+            const int depth) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4 *cam_s = reinterpret_cast<float4 *>(smem_raw);                    // (campos xyz, scale) per staged view
+    float *sh_s = reinterpret_cast<float *>(smem_raw + SHC_VIEWS * sizeof(float4));
+    const int tid = threadIdx.x;
+    const uint32_t row_f = (uint32_t)c.M * 3u, want_f = (uint32_t)(c.M < 16 ? c.M : 16) * 3u;
+    const int total = blocks_per_scene * c.S;
+    for (int blk = blockIdx.x; blk < total; blk += gridDim.x) {
+        const int scene = blk / blocks_per_scene, g0 = (blk - scene * blocks_per_scene) * SHC_THREADS;
+        const int n = min(SHC_THREADS, c.P - g0);
+        const bool active = tid < n;
+        const size_t sg = (size_t)scene * c.P + g0 + tid;
+        __syncthreads();   // the previous block's rows and cameras have been read by everybody
+        {
+            // `depth` pieces per thread and group, two groups in flight: the reads this SM has outstanding over PCIe stay
+            // bounded (an SM whose miss queue is full of 2-microsecond host reads stalls every other warp's memory
+            // instructions -- the geometry kernel and the sort run on the same SMs)
+            const float *src = shs + ((size_t)scene * c.P + g0) * row_f;
+            const uint32_t nfl = (uint32_t)n * row_f, nq = nfl >> 2;
+            const float4 *src4 = reinterpret_cast<const float4 *>(src);
+            int in_group = 0;
+            for (uint32_t q0 = 0; q0 < nq; q0 += SHC_THREADS) {   // (uniform trip count: the waits below are collective-free but cheap)
+                const uint32_t q = q0 + tid;
+                if (q < nq) {
+                    const uint32_t f0 = q << 2, r = f0 / row_f, c0 = f0 - r * row_f;
+                    if (c0 < want_f || c0 + 3u >= row_f) cp_async16(sh_s + f0, src4 + q);
+                }
+                if (++in_group == depth) {
+                    cp_async_commit();
+                    cp_async_wait<1>();
+                    in_group = 0;
+                }
+            }
+            for (uint32_t f = (nq << 2) + tid; f < nfl; f += SHC_THREADS)
+                if (f % row_f < want_f) cp_async4(sh_s + f, src + f);
+            cp_async_commit();
+        }
+        float3 mean = make_float3(0.f, 0.f, 0.f);
+        if (active) mean = make_float3(means3D[sg * 3 + 0], means3D[sg * 3 + 1], means3D[sg * 3 + 2]);
+        for (int v0 = 0; v0 < c.VPS; v0 += SHC_VIEWS) {
+            const int nv = min(SHC_VIEWS, c.VPS - v0);
+            if (v0) __syncthreads();
+            for (int t = tid; t < nv; t += SHC_THREADS) {
+                const int v = scene * c.VPS + v0 + t;
+                cam_s[t] = make_float4(c.campos[v * 3 + 0], c.campos[v * 3 + 1], c.campos[v * 3 + 2], c.view_scale ? c.view_scale[v] : 1.0f);
+            }
+            if (v0 == 0) cp_async_wait<0>();
+            __syncthreads();
+            if (!active) continue;
+            const float *sh = sh_s + (size_t)tid * row_f;
+            for (int vi = 0; vi < nv; vi++) {
+                const float4 cam = cam_s[vi];
+                const size_t o = (size_t)(scene * c.VPS + v0 + vi) * c.P + g0 + tid;
+                const float3 m = make_float3(mean.x * cam.w, mean.y * cam.w, mean.z * cam.w);
+                const float cp[3] = {cam.x, cam.y, cam.z};
+                uint32_t clamped = 0;
+                const float3 rgb = eval_sh(c.deg, sh, sh_view_dir(m, cp), clamped);
+                reinterpret_cast<float2 *>(&rec1[o])[1] = make_float2(rgb.x, rgb.y);
+                reinterpret_cast<float *>(&rec2[o])[0] = rgb.z;
+                if (clamp_out) clamp_out[o] = (uint8_t)clamped;
+            }
+        }
+    }
+}
+
 __global__ void k_mark_visible(const DevCfg c, const float *__restrict__ means3D, uint8_t *__restrict__ present) {
     __shared__ ViewCam cam;
     const int v = blockIdx.y;
@@ -350,11 +469,11 @@ int launch_preprocess(const DevCfg &c, const DevInputs &in, float4 *rec0, float4
     // M > 16, on request: 16-byte pieces at the rows' own stride -- if every CTA's block starts 16-byte aligned (CTAs cover
     // 128 rows = 1536 M bytes, so the first one decides -- per scene); else the compacting 4-byte gather
     int sh_raw16 = 0;
-    if (in.shs && c.M > 16 && (variant & 2)) {
+    if (in.shs && c.M > 16 && (variant & 2) && !(variant & 4)) {
         const uintptr_t first = reinterpret_cast<uintptr_t>(in.shs) + (size_t)g_begin * c.M * 12;
         sh_raw16 = (first & 15u) == 0 && (c.S == 1 || ((size_t)c.P * c.M * 12) % 16 == 0);
     }
-    const size_t smem = PRE_SMEM_HDR + (in.shs ? (size_t)PRE_THREADS * ((c.M <= 16 || sh_raw16) ? c.M * 3 : 49) * 4 : 0);
+    const size_t smem = PRE_SMEM_HDR + ((in.shs && !(variant & 4)) ? (size_t)PRE_THREADS * ((c.M <= 16 || sh_raw16) ? c.M * 3 : 49) * 4 : 0);
     if (smem > (size_t)227 * 1024) return gs_set_error(GS_ERR_INVALID, "too many SH coefficients per Gaussian for the staging buffer");
     auto launch = [&](auto kern) -> int {
         GS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -362,9 +481,43 @@ int launch_preprocess(const DevCfg &c, const DevInputs &in, float4 *rec0, float4
         return GS_OK;
     };
     int rc;
-    if (in.shs) rc = more_ctas ? launch(k_preprocess<true, 6>) : launch(k_preprocess<true, 5>);
-    else rc = more_ctas ? launch(k_preprocess<false, 6>) : launch(k_preprocess<false, 5>);
+    if (variant & 4) rc = more_ctas ? launch(k_preprocess<0, 6>) : launch(k_preprocess<0, 5>);   // geometry only
+    else if (in.shs) rc = more_ctas ? launch(k_preprocess<2, 6>) : launch(k_preprocess<2, 5>);
+    else rc = more_ctas ? launch(k_preprocess<1, 6>) : launch(k_preprocess<1, 5>);
     if (rc != GS_OK) return rc;
+    GS_CUDA_OK(cudaGetLastError());
+    return GS_OK;
+}
+
+bool sh_colour_supported(const DevCfg &c, const DevInputs &in) {
+    return in.shs && c.M > 16 && (reinterpret_cast<uintptr_t>(in.shs) & 15u) == 0 &&
+           (c.S == 1 || ((size_t)c.P * c.M * 12) % 16 == 0) &&
+           SHC_VIEWS * sizeof(float4) + (size_t)SHC_THREADS * c.M * 12 <= (size_t)72 * 1024;
+}
+
+int launch_sh_colour(const DevCfg &c, const DevInputs &in, float4 *rec1, float4 *rec2, uint8_t *clamp_out, cudaStream_t st) {
+    if (c.P == 0 || c.V == 0) return GS_OK;
+    if (!sh_colour_supported(c, in)) return gs_set_error(GS_ERR_INVALID, "k_sh_colour: unsupported SH layout");
+    static int sms_of_device[64] = {};
+    int dev = 0;
+    GS_CUDA_OK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && sms_of_device[dev] == 0)
+        GS_CUDA_OK(cudaDeviceGetAttribute(&sms_of_device[dev], cudaDevAttrMultiProcessorCount, dev));
+    const int sms = (dev >= 0 && dev < 64 && sms_of_device[dev] > 0) ? sms_of_device[dev] : 148;
+    const int bps = (c.P + SHC_THREADS - 1) / SHC_THREADS;
+    const long long total = (long long)bps * c.S;
+    // Two CTAs per SM, two 16-byte pieces per thread and group (8 KB of host reads outstanding per CTA).  Measured on C2
+    // inside gs_render_host (scripts/probes/shc_sweep.sh; colour kernel / geometry / sort / whole call, ms):
+    //   3 CTAs, whole block at once  2.63 / 2.63 / 0.108 (after it) / 3.59-3.65   <- the other kernels starve until it ends
+    //   1 CTA,  2 pieces             2.71 / 0.50 / 0.33 / 3.60
+    //   2 CTAs, 2 pieces             2.84 / 1.02 / 0.67 / 3.61
+    //   1 CTA,  1 piece              2.87 / 0.33 / 0.20 / 3.84
+    // (alone, geometry takes 0.19 and the sort 0.107: the host reads in flight slow every memory instruction of the SM).
+    const int per_sm = 2, depth = 2;
+    const int grid = (int)(total < (long long)sms * per_sm ? total : (long long)sms * per_sm);
+    const size_t smem = SHC_VIEWS * sizeof(float4) + (size_t)SHC_THREADS * c.M * 12;
+    GS_CUDA_OK(cudaFuncSetAttribute(k_sh_colour, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_sh_colour<<<grid, SHC_THREADS, smem, st>>>(c, in.means3D, in.shs, rec1, rec2, clamp_out, bps, depth < 1 ? 1 : depth);
     GS_CUDA_OK(cudaGetLastError());
     return GS_OK;
 }

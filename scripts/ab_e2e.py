@@ -55,7 +55,7 @@ else:
 for _ in range(5):
     call()
 res = {n: [] for n in variants}
-for rep in range(5):
+for rep in range(int(os.environ.get("AB_REPS", 5))):
     for n in variants:
         cfg.tuning = word(n)
         call()
@@ -64,5 +64,16 @@ for rep in range(5):
         for _ in range(20):
             call()
         res[n].append((time.perf_counter() - t0) / 20 * 1e3)
+if os.environ.get("AB_STAGES"):   # per-stage device times of each variant (events recorded by the library)
+    rasterizer.set_profiling(True, dev)
+    for n in variants:
+        cfg.tuning = word(n)
+        acc = {}
+        for _ in range(6):
+            call()
+            for k_, v_ in rasterizer.stage_ms(dev).items():
+                acc.setdefault(k_, []).append(v_)
+        print(n, {k_: round(sorted(v_)[len(v_) // 2], 4) for k_, v_ in acc.items()})
+    rasterizer.set_profiling(False, dev)
 for n in variants:
-    print(n, " ".join(f"{x:.3f}" for x in res[n]), f"median {sorted(res[n])[len(res[n]) // 2]:.3f} ms")
+    print(n, " ".join(f"{x:.3f}" for x in res[n]), f"median {sorted(res[n])[len(res[n]) // 2]:.3f} ms  min {min(res[n]):.3f} ms")

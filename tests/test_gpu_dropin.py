@@ -200,16 +200,17 @@ def test_host_buffer_entry_matches_device_entry(P):
                                                torch.cuda.current_stream(dev).cuda_stream))
         assert torch.equal(pc, c2.cpu()) and torch.equal(pr, r2.cpu()) and torch.equal(pd, d2.cpu())
     cfg.tuning = 0
-    # PINNED input buffers: preprocess pulls the SH pieces it wants straight out of the host buffer (zero-copy feed,
-    # 16-byte pieces at the rows' own stride); GS_TUNE_NO_ZERO_COPY = the copy engine's pieced upload,
-    # GS_TUNE_PRE_SH_RAW16 = the same staging on the device copy -- same bytes out every way.  A view of the pinned block that
-    # starts one row in (only 4-byte aligned) must take the upload path by itself.
+    # PINNED input buffers (default): geometry-only preprocess + tile sort on the launch stream while k_sh_colour pulls the
+    # SH pieces it wants straight out of the host buffer on a second stream (zero-copy feed, split pipeline);
+    # GS_TUNE_NO_SPLIT_COLOUR = one fused preprocess doing the pull; GS_TUNE_NO_ZERO_COPY = the copy engine's pieced upload;
+    # GS_TUNE_PRE_SH_RAW16 = the pull's staging on the device copy -- same bytes out every way.  A view of the pinned block
+    # that starts one row in (only 4-byte aligned) must take the upload path by itself.
     pin = {k: v.pin_memory() for k, v in host.items()}
     gin_pin = _capi.GsInputs(means3D=pin["means3D"].data_ptr(), opacities=pin["opacities"].data_ptr(),
                              shs=pin["shs"].data_ptr(), cov3D_precomp=pin["cov3D_precomp"].data_ptr())
-    for tuning in (0, _capi.GS_TUNE_NO_ZERO_COPY, _capi.GS_TUNE_NO_ZERO_COPY | _capi.GS_TUNE_PRE_SH_RAW16):
+    for tuning in (0, _capi.GS_TUNE_NO_SPLIT_COLOUR, _capi.GS_TUNE_NO_ZERO_COPY, _capi.GS_TUNE_NO_ZERO_COPY | _capi.GS_TUNE_PRE_SH_RAW16):
         cfg.tuning = tuning
-        for _ in range(2):
+        for _ in range(3):   # (exact, trial and stratified binning under every feed)
             pc.zero_(); pr.zero_(); pd.zero_()
             _capi.check(_capi.lib().gs_render_host(ctx, ctypes.byref(cfg), ctypes.byref(gin_pin), ctypes.byref(gpin),
                                                    torch.cuda.current_stream(dev).cuda_stream))
