@@ -252,7 +252,15 @@ def main():
     hin = _capi.GsInputs(means3D=host["means3D"].data_ptr(), opacities=host["opacities"].data_ptr(),
                          shs=host["shs"].data_ptr(), cov3D_precomp=host["cov3D_precomp"].data_ptr())
     hout = _capi.GsOutputs(color=out_color.data_ptr(), radii=out_radii.data_ptr(), depth=None)
-    h2d = sum(host[k].numel() * 4 for k in host)
+    # Bytes that cross PCIe per step.  Everything but the SH block is copied whole; of the SH block (pinned, M = 25)
+    # k_sh_colour pulls the 16-byte pieces that hold a coefficient of bands 0..3 straight out of the host buffer
+    # (zero-copy feed): 51 of every 75 pieces (4 rows).  --tuning 131072 (GS_TUNE_NO_ZERO_COPY) copies it whole instead.
+    zero_copy = D_SH > 16 and not (args.tuning & _capi.GS_TUNE_NO_ZERO_COPY)
+    row_f = D_SH * 3
+    pulled16 = sum(1 for q in range(row_f) if (4 * q) % row_f < 48 or (4 * q) % row_f + 3 >= row_f)   # per 4 rows = row_f pieces
+    sh_bytes = host["shs"].numel() * 4
+    sh_crossing = sh_bytes * pulled16 // row_f if zero_copy else sh_bytes
+    h2d = sum(host[k].numel() * 4 for k in host if k != "shs") + sh_crossing
     d2h = out_color.numel() * 4 + out_radii.numel() * 4
     stream = torch.cuda.current_stream(dev)
     ctx = rasterizer.current_context(dev)
@@ -606,7 +614,9 @@ def main():
             "views_per_sec": VIEWS * world * args.steps / (ms_fwd * 1e-3),
             "e2e": {"value": gauss_per_step * args.steps / (ms_e2e * 1e-3), "unit": "Gaussians/s",
                     "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "gs_render_host (C ABI, pinned host buffers)" if world == 1 else
+                    "api": ("gs_render_host (C ABI, pinned host buffers; SH block pulled zero-copy by k_sh_colour: "
+                            f"{sh_crossing} of its {sh_bytes} bytes requested in 16-byte pieces, the rest of the inputs copied)"
+                            if zero_copy else "gs_render_host (C ABI, pinned host buffers, everything copied)") if world == 1 else
                            "SharedCloudUploader (1/N of the cloud per rank over PCIe + NCCL all-gather over NVLink) + "
                            "rasterize_batch + D2H of the results; pinned buffers allocated on the GPU's NUMA node",
                     "numa_cpus_rank0": len(numa_cpus)},
