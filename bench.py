@@ -300,7 +300,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps, warmup):
+    per_rank_ms = {}
+
+    def timed(fn, steps, warmup, tag=None):
         for _ in range(warmup):
             fn()
         barrier()
@@ -312,6 +314,9 @@ def main():
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
+            every = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(every, ms)                      # each rank's own device time: what the MAX below is taken over
+            per_rank_ms[tag] = [float(t.item()) / steps for t in every]
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
@@ -332,10 +337,10 @@ def main():
 
     sampler = ClockSampler(local)
     sampler.start()
-    ms_fwd = timed(fwd, args.steps, args.warmup)
+    ms_fwd = timed(fwd, args.steps, args.warmup, "fwd")
     launches_fwd = rasterizer.last_stats(dev)["kernel_launches"]   # of the last timed step (steady state)
-    ms_e2e = timed(e2e, args.steps, args.warmup)
-    ms_fb = timed(fwd_bwd, args.steps, args.warmup)
+    ms_e2e = timed(e2e, args.steps, args.warmup, "e2e")
+    ms_fb = timed(fwd_bwd, args.steps, args.warmup, "fwd_bwd")
     stats_fb = rasterizer.last_stats(dev)
 
     # ---- moving cloud: every step renders a different cloud (training moves the Gaussians between steps), so the bucket
@@ -612,6 +617,7 @@ def main():
                        "parallelism": f"views sharded over {world} GPU(s), no data-path collective",
                        "l2": "inputs+intermediates per step (~360 MB for C2) exceed the 126 MB L2; no explicit flush"},
             "views_per_sec": VIEWS * world * args.steps / (ms_fwd * 1e-3),
+            "per_rank_ms_per_step": per_rank_ms or None,   # N > 1: every rank's own device time per step (value uses the max)
             "e2e": {"value": gauss_per_step * args.steps / (ms_e2e * 1e-3), "unit": "Gaussians/s",
                     "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": ("gs_render_host (C ABI, pinned host buffers; SH block pulled zero-copy by k_sh_colour: "
