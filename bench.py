@@ -375,7 +375,7 @@ def main():
             fwd_moving()                                            # variant: the sticky capacities ratchet up to the largest
         state.update(calls=0)                                       # (each growth re-allocates ~100 MB of buckets, ~1 ms)
         redos0 = rasterizer.last_stats(dev)["overflow_redos"]
-        ms_mov = timed(fwd_moving, args.steps, args.warmup)
+        ms_mov = timed(fwd_moving, args.steps, args.warmup, "moving_cloud")
         state["overflows"] = rasterizer.last_stats(dev)["overflow_redos"] - redos0
         rasterizer.set_profiling(True, dev)
         acc_m = {}
@@ -427,8 +427,8 @@ def main():
 
         for _ in range(3):
             fwd4()                      # exact -> trial -> steady state
-        ms4_first = timed(fwd4_counted, steps4, 3)
-        ms4 = timed(fwd4_counted, steps4, 1)     # reported: the second timed loop (the first one is kept as `first_loop_ms`)
+        ms4_first = timed(fwd4_counted, steps4, 3, "c4_first_loop")
+        ms4 = timed(fwd4_counted, steps4, 1, "c4")     # reported: the second timed loop (the first one is kept as `first_loop_ms`)
         st4 = rasterizer.last_stats(dev)
         # per-rank view of the same loop (its own CUDA events), gathered: who is the slowest and why
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
