@@ -18,7 +18,7 @@ dev = torch.device("cuda:0")
 sc = make_scene(P, V, HW, HW, seed=0).to(dev)
 vb = make_view_batch(sc.extrinsics, sc.intrinsics, sc.near, sc.far)
 bs = BatchSettings(image_height=HW, image_width=HW, viewmatrix=vb.viewmatrix, projmatrix=vb.projmatrix, campos=vb.campos,
-                   bg=sc.background, sh_degree=4, tanfov=vb.tanfov)
+                   bg=sc.background, sh_degree=4, tanfov=vb.tanfov, tuning=int(os.environ.get("GS_TUNING", 0)))
 means = sc.means[None].clone().requires_grad_(bwd)
 opac = sc.opacities[None].clone().requires_grad_(bwd)
 shs = sc.harmonics.permute(0, 2, 1).contiguous()[None].requires_grad_(bwd)
