@@ -553,7 +553,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
         if ((e = join_colour()) != cudaSuccess) return fail(gs_set_cuda_error(e, "cudaStreamWaitEvent(colour)", __FILE__, __LINE__));
         {
             StageTimer t(ctx, GS_STAGE_COMPOSITE, st);
-            rc = launch_composite_fwd(c, *s, out->color, out->depth, st, (cfg->tuning & GS_TUNE_FWD_WS) ? 2 : ((cfg->tuning & GS_TUNE_FWD_GROUPS) ? 3 : 0));
+            rc = launch_composite_fwd(c, *s, out->color, out->depth, st, (cfg->tuning & GS_TUNE_FWD_WS) ? 2 : 0);
             if (rc != GS_OK) return fail(rc);
         }
         e = cudaEventSynchronize(ctx->ev_info);  // the one host sync of the forward (verification only)
@@ -685,7 +685,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     }
     {
         StageTimer t(ctx, GS_STAGE_COMPOSITE, st);
-        rc = launch_composite_fwd(c, *s, out->color, out->depth, st, (cfg->tuning & GS_TUNE_FWD_WS) ? 2 : ((cfg->tuning & GS_TUNE_FWD_GROUPS) ? 3 : 0));
+        rc = launch_composite_fwd(c, *s, out->color, out->depth, st, (cfg->tuning & GS_TUNE_FWD_WS) ? 2 : 0);
         if (rc != GS_OK) return fail(rc);
         ctx->stats.kernel_launches += 1;
     }

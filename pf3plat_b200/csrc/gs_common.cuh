@@ -4,9 +4,8 @@
 // V*P entries each, written by preprocess and gathered by the compositors with 16-byte loads:
 //   rec0 = (x_pix, y_pix, -0.5*log2e*conic_a, -log2e*conic_b)
 //   rec1 = (-0.5*log2e*conic_c, opacity, r, g)
-//   rec2 = (b, z_cam, reach2, ext)    reach2 = -(log2(255*opacity) + margin): a pixel can receive the Gaussian
-//                                     only where log2 G >= reach2 (see gs_box_reaches); ext = two fp16 (rounded up):
-//                                     half-extents in x and y of the bounding box of that region
+//   rec2 = (b, z_cam, reach2, 0)      reach2 = -(log2(255*opacity) + margin): a pixel can receive the Gaussian
+//                                     only where log2 G >= reach2 (see gs_box_reaches)
 // The conic is stored pre-scaled so that the compositors get log2(G) = power*log2(e) with five FP ops and feed
 // it straight to ex2.approx (gs_power2 / gs_ex2 below; forward and backward share them bit for bit).
 // plus meta[V*P] (uint8: bits 0-2 = SH clamp flags, bit 3 = visible).
@@ -115,7 +114,7 @@ int bin_sort_fallback(const DevCfg &c, int64_t D, const float4 *rec0, const floa
                       cudaStream_t st);
 
 int launch_composite_fwd(const DevCfg &c, const GsSaved &s, float *color, float *depth, cudaStream_t st,
-                         int variant = 0 /* 2: the persistent warp-specialised kernel (GS_TUNE_FWD_WS); 3: group queues (GS_TUNE_FWD_GROUPS) */);
+                         int variant = 0 /* 2: the persistent warp-specialised kernel (GS_TUNE_FWD_WS) */);
 int launch_composite_bwd(const DevCfg &c, const GsSaved &s, const float *dL_dcolor, const float *dL_ddepth,
                          float *grad_acc /* [V*P*GS_ACC_STRIDE], zeroed */, cudaStream_t st,
                          int variant = 0 /* 1: the round-1 kernel (GS_TUNE_BWD_V1) */);

@@ -20,8 +20,6 @@
 // pipeline over groups of views (k_tile_sort of group g+1 on a side stream under the compositing of group g):
 // 1.21 ms per C2 forward vs 1.01 ms serial -- the co-resident sort CTAs take registers/shared memory from the
 // compositor without filling its idle issue slots.
-#include <cuda_fp16.h>
-
 #include "gs_common.cuh"
 
 namespace {
@@ -136,164 +134,6 @@ k_composite_fwd(const DevCfg c, const float4 *__restrict__ rec0, const float4 *_
         }
     }
     cp_async_wait<0>();  // nothing of ours may still be in flight into shared memory when the CTA retires
-
-    if (inside) {
-        const size_t hw = (size_t)c.H * c.W;
-        const size_t pix = (size_t)py * c.W + px;
-        const float *bg = c.bg ? c.bg + (size_t)v * 3 : nullptr;
-        float *out = color + (size_t)v * 3 * hw + pix;
-        out[0] = C0 + T * (bg ? bg[0] : 0.f);
-        out[hw] = C1 + T * (bg ? bg[1] : 0.f);
-        out[2 * hw] = C2 + T * (bg ? bg[2] : 0.f);
-        if (DEPTH) depth[(size_t)v * hw + pix] = Dz;
-        final_T[(size_t)v * hw + pix] = T;
-        n_contrib[(size_t)v * hw + pix] = last;
-    }
-}
-
-
-// ---------------------------------------------------------------------------------------------------------
-// Group-queue variant (GS_TUNE_FWD_GROUPS): eight 2x2-pixel lane groups per warp, each walking its OWN survivors
-// ---------------------------------------------------------------------------------------------------------
-// v1's per-survivor loop runs with 7.8 of 32 lanes on a live pixel: a survivor of the 8x4 block typically covers a
-// quarter of it, and all 32 lanes step through every survivor.  Here the warp's block is split into eight 2x2-pixel
-// groups of four lanes; the cull additionally derives, per candidate, which groups the bounding box of its alpha >= 1/255
-// region touches (rec2.w: fp16 half-extents written by preprocess; four column bits x two row bits, six ballots per 32
-// candidates), every group gets its own survivor mask per chunk of 32 (shared memory, [chunk][group]), and after the whole
-// batch of 256 has been culled the groups walk their own masks independently inside one converged loop -- a group steps
-// only through the survivors that can touch its four pixels.  Simulated on C2 (bounding-box masks, balance taken per batch):
-// 0.61 iterations per block-level survivor instead of 1.  Order within a group is list order, arithmetic is v1's: images,
-// final T and contributor counts are bit-identical (tested).
-constexpr int CG_CHUNKS = CF_BATCH / 32;
-
-template <bool DEPTH, int MINB>
-__global__ void __launch_bounds__(CF_THREADS, MINB)
-k_composite_fwd_gq(const DevCfg c, const float4 *__restrict__ rec0, const float4 *__restrict__ rec1,
-                   const float4 *__restrict__ rec2, const uint32_t *__restrict__ point_list,
-                   const uint2 *__restrict__ ranges, float *__restrict__ color, float *__restrict__ depth,
-                   float *__restrict__ final_T, uint32_t *__restrict__ n_contrib) {
-    __shared__ CfStage stage[2];
-    __shared__ uint32_t gmask[CF_THREADS / 32][CG_CHUNKS][8];
-
-    const int v = blockIdx.y;
-    const int tile = blockIdx.x;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int bx = (tile % c.gx) * GS_TILE + (warp & 1) * 8;   // this warp's 8x4 pixel block
-    const int by = (tile / c.gx) * GS_TILE + (warp >> 1) * 4;
-    const int grp = lane >> 2, gi = grp & 3, gj = grp >> 2;    // group = 2x2 pixels at columns 2 gi.., rows 2 gj..
-    const int px = bx + 2 * gi + (lane & 1), py = by + 2 * gj + ((lane >> 1) & 1);
-    const bool inside = px < c.W && py < c.H;
-    const float pxf = (float)px, pyf = (float)py;
-    const float bx0 = (float)bx, bx1 = (float)(bx + 7), by0 = (float)by, by1 = (float)(by + 3);
-
-    const uint2 range = ranges[(size_t)v * c.ntiles + tile];
-    const uint32_t total = range.y - range.x;
-    const uint32_t nbatches = (total + CF_BATCH - 1) / CF_BATCH;
-    const size_t rbase = (size_t)v * c.P;
-    const uint32_t stage_addr = smem_u32(&stage[0].rec[0][0]);
-    const uint32_t gm_addr = smem_u32(&gmask[warp][0][grp]);     // this group's mask of chunk 0; chunks are 32 bytes apart
-
-    auto gather = [&](uint32_t b, uint32_t id) {
-        if (b * CF_BATCH + tid < total) {
-            const size_t r = rbase + id;
-            float4 *dst = &stage[b & 1].rec[tid][0];
-            cp_async16(dst, rec0 + r);
-            cp_async16(dst + 1, rec1 + r);
-            cp_async16(dst + 2, rec2 + r);
-        }
-        cp_async_commit();
-    };
-    auto load_id = [&](uint32_t b) -> uint32_t {
-        const uint32_t e = b * CF_BATCH + tid;
-        return e < total ? point_list[range.x + e] : 0u;
-    };
-
-    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dz = 0.f;
-    uint32_t last = 0;
-    bool done = !inside;
-    bool warp_done = false;
-
-    gather(0, load_id(0));
-    uint32_t id_next = load_id(1);
-    for (uint32_t b = 0; b < nbatches; b++) {
-        if (__syncthreads_and(done)) break;
-        gather(b + 1, id_next);
-        id_next = load_id(b + 2);
-        cp_async_wait<1>();
-        __syncthreads();
-        if (warp_done) continue;
-        const uint32_t nb = min((uint32_t)CF_BATCH, total - b * CF_BATCH);
-        const uint32_t nch = (nb + 31u) >> 5;
-        const uint32_t pos0 = b * CF_BATCH + 1;
-        const uint32_t rec_addr = stage_addr + (b & 1u) * (uint32_t)sizeof(CfStage);
-        // ---- cull: lane k <-> candidate k of the chunk; block-level exact test, group-level bounding-box test ----
-        for (uint32_t ch = 0; ch < nch; ch++) {
-            const uint32_t j = (ch << 5) + lane;
-            bool hit = false;
-            float xl = 0.f, xr = 0.f, yl = 0.f, yr = 0.f;
-            if (j < nb) {
-                const uint32_t a = rec_addr + j * 48u;
-                const float4 g0 = lds128(a);
-                const float2 rz = lds64(a + 40u);   // (reach2, packed half-extents)
-                hit = gs_box_reaches(g0.x, g0.y, g0.z, g0.w, lds32(a + 16u), rz.x, bx0, bx1, by0, by1);
-                const float2 ext = __half22float2(*reinterpret_cast<const __half2 *>(&rz.y));
-                xl = (g0.x - ext.x) - bx0; xr = (g0.x + ext.x) - bx0;   // extent of the footprint relative to the block
-                yl = (g0.y - ext.y) - by0; yr = (g0.y + ext.y) - by0;
-            }
-            // columns 2i..2i+1 touched iff xr >= 2i and xl <= 2i+1; rows likewise
-            const uint32_t cm0 = __ballot_sync(0xffffffffu, hit && xl <= 1.0f);
-            const uint32_t cm1 = __ballot_sync(0xffffffffu, hit && xr >= 2.0f && xl <= 3.0f);
-            const uint32_t cm2 = __ballot_sync(0xffffffffu, hit && xr >= 4.0f && xl <= 5.0f);
-            const uint32_t cm3 = __ballot_sync(0xffffffffu, hit && xr >= 6.0f);
-            const uint32_t rm0 = __ballot_sync(0xffffffffu, yl <= 1.0f);
-            const uint32_t rm1 = __ballot_sync(0xffffffffu, yr >= 2.0f);
-            const uint32_t cm = (gi & 2) ? ((gi & 1) ? cm3 : cm2) : ((gi & 1) ? cm1 : cm0);
-            const uint32_t mine = cm & (gj ? rm1 : rm0);
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(gm_addr + ch * 32u), "r"(mine) : "memory");   // (four lanes, same word, same value)
-        }
-        __syncwarp();
-        // ---- walk: every group through its own survivors, all groups inside one converged loop ----
-        uint32_t ch = 0, m = 0;
-        auto advance = [&]() -> bool {   // next chunk with work for this group; false when the batch is exhausted
-            while (m == 0u && ch < nch) {
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m) : "r"(gm_addr + ch * 32u));
-                ch++;
-            }
-            return m != 0u;
-        };
-        bool have = !done && advance();
-        while (__any_sync(0xffffffffu, have)) {
-            if (have) {
-                const uint32_t bit = (uint32_t)__ffs(m) - 1u;
-                m &= m - 1u;
-                const uint32_t idx = ((ch - 1u) << 5) + bit;
-                const uint32_t a = rec_addr + idx * 48u;
-                const float4 q0 = lds128(a), q1 = lds128(a + 16u);
-                const float dx = q0.x - pxf, dy = q0.y - pyf;
-                const float p2 = gs_power2(q0.z, q0.w, q1.x, dx, dy);
-                const float alpha = fminf(GS_ALPHA_MAX, q1.y * gs_ex2(p2));
-                if (p2 <= 0.0f && alpha >= GS_ALPHA_MIN) {
-                    const float test_T = T * (1.0f - alpha);
-                    if (test_T < GS_T_MIN) {
-                        done = true;
-                    } else {
-                        const float2 q2 = lds64(a + 32u);
-                        const float w = alpha * T;
-                        C0 = fmaf(q1.z, w, C0);
-                        C1 = fmaf(q1.w, w, C1);
-                        C2 = fmaf(q2.x, w, C2);
-                        if (DEPTH) Dz = fmaf(q2.y, w, Dz);
-                        T = test_T;
-                        last = pos0 + idx;
-                    }
-                }
-                have = !done && advance();
-            }
-        }
-        __syncwarp();   // the masks may be overwritten by the next batch's cull
-        if (__all_sync(0xffffffffu, done)) warp_done = true;
-    }
-    cp_async_wait<0>();
 
     if (inside) {
         const size_t hw = (size_t)c.H * c.W;
@@ -538,15 +378,6 @@ int launch_composite_fwd(const DevCfg &c, const GsSaved &s, float *color, float 
         return GS_OK;
     }
     dim3 grid(c.ntiles, c.V);
-    if (variant == 3) {
-        auto launch_gq = [&](auto kern) {
-            kern<<<grid, CF_THREADS, 0, st>>>(c, s.rec0, s.rec1, s.rec2, s.point_list, s.ranges, color, depth, s.final_T, s.n_contrib);
-        };
-        if (c.flags & GS_FLAG_DEPTH) launch_gq(k_composite_fwd_gq<true, 6>);
-        else launch_gq(k_composite_fwd_gq<false, 6>);
-        GS_CUDA_OK(cudaGetLastError());
-        return GS_OK;
-    }
     // 6 resident CTAs per SM (39 registers).  Bounding the registers to 32 for 8 CTAs/SM (28 B of spills) was slower on
     // C2: 0.324 vs 0.314 ms -- issue-bound, like the backward.
     constexpr int MINB = 6;

@@ -9,8 +9,6 @@
 //  * outputs are three float4 SoA planes written with 16-byte stores;
 //  * tile binning keeps, of upstream's 3-sigma square, only the tiles the alpha >= 1/255 ellipse really reaches
 //    (exact box test), so tile lists only hold Gaussians that can contribute (identical pixels, -27 % instances).
-#include <cuda_fp16.h>
-
 #include "gs_common.cuh"
 
 namespace {
@@ -156,13 +154,7 @@ __device__ __forceinline__ void project_splat(const DevCfg &c, const ViewCam &ca
         out.rect = make_ushort4((unsigned short)rminx, (unsigned short)rminy, (unsigned short)rmaxx, (unsigned short)rmaxy);
     out.r0 = make_float4(px, py, hA, nB);
     out.r1 = make_float4(hC, opac, rgb.x, rgb.y);
-    // half-extents (pixels) of the bounding box of the alpha >= 1/255 ellipse  d^T conic d <= tau  (conic^-1 = cov2D, so the
-    // extents are sqrt(tau * a), sqrt(tau * cc)), rounded UP to fp16 with a little slack: the group-queue compositor's
-    // cheap per-pixel-group test (gs_composite_fwd.cu); never tighter than gs_box_reaches' own threshold (same tau)
-    const float taup = fmaxf(tau, 0.0f);
-    const __half2 ext = __halves2half2(__float2half_ru(fminf(1.01f * sqrtf(taup * a) + 0.02f, 60000.0f)),
-                                       __float2half_ru(fminf(1.01f * sqrtf(taup * cc) + 0.02f, 60000.0f)));
-    out.r2 = make_float4(rgb.z, pv.z, reach2, __uint_as_float(*reinterpret_cast<const uint32_t *>(&ext)));
+    out.r2 = make_float4(rgb.z, pv.z, reach2, 0.0f);
 }
 
 // MINB: resident CTAs per SM the register allocation is bounded for.  Unbounded the kernel takes 96 registers (5 CTAs/SM,

@@ -257,8 +257,8 @@ def test_compositor_variants_agree():
     """Round-2 kernels against the round-1 kernels they replace (kept behind tuning flags for A/B): the persistent
     warp-specialised forward compositor gives bit-identical images, final T and contributor counts (same arithmetic in
     the same order); the pair-matrix backward gives the same gradients up to the re-association of the sums."""
-    from pf3plat_b200._capi import (GS_TUNE_BWD_OCC4, GS_TUNE_BWD_V1, GS_TUNE_FWD_GROUPS, GS_TUNE_FWD_WS, GS_TUNE_PBWD_2PHASE,
-                                    GS_TUNE_PRE_OCC6, GS_TUNE_PRE_SH_RAW16)
+    from pf3plat_b200._capi import (GS_TUNE_BWD_OCC4, GS_TUNE_BWD_V1, GS_TUNE_FWD_WS, GS_TUNE_PBWD_2PHASE, GS_TUNE_PRE_OCC6,
+                                    GS_TUNE_PRE_SH_RAW16)
     from pf3plat_b200.cameras import make_view_batch
     from pf3plat_b200.rasterizer import BatchSettings, rasterize_batch
     dev = _dev()
@@ -272,7 +272,7 @@ def test_compositor_variants_agree():
         bg = torch.rand(d.background.shape, device=dev)
         outs, grads = {}, {}
         variants = (GS_TUNE_FWD_WS, GS_TUNE_BWD_V1, GS_TUNE_FWD_WS | GS_TUNE_BWD_V1, GS_TUNE_BWD_OCC4, GS_TUNE_PBWD_2PHASE,
-                    GS_TUNE_PRE_OCC6, GS_TUNE_PRE_SH_RAW16, GS_TUNE_FWD_GROUPS)
+                    GS_TUNE_PRE_OCC6, GS_TUNE_PRE_SH_RAW16)
         for tuning in (0,) + variants:
             bs = BatchSettings(image_height=h, image_width=w, viewmatrix=vb.viewmatrix, projmatrix=vb.projmatrix,
                                campos=vb.campos, bg=bg, sh_degree=4, tanfov=vb.tanfov, view_scale=vb.scale,
