@@ -64,6 +64,43 @@ for rep in range(6):
     states.append(last_stats(dev)["speculative"])
 print("ok pixel-aligned, speculative per call:", states)
 
+# ---- gs_render_host with pinned buffers: zero-copy feed (k_sh_colour pulling out of host memory + geometry-only preprocess),
+# the fused pull, and the copy-engine path; one scene and two scenes ----
+import ctypes  # noqa: E402
+
+from pf3plat_b200 import _capi, rasterizer  # noqa: E402
+
+for (S, P, V, hw) in [(1, 4100, 3, (40, 56)), (2, 1001, 4, (32, 32))]:
+    scs = [make_scene(P, V // S, *hw, seed=50 + k) for k in range(S)]
+    vbs = [make_view_batch(sc.extrinsics, sc.intrinsics, sc.near, sc.far) for sc in scs]
+    cat = lambda f: torch.cat([f(k) for k in range(S)]).contiguous().float().pin_memory()
+    cov6 = lambda c: torch.stack([c[:, 0, 0], c[:, 0, 1], c[:, 0, 2], c[:, 1, 1], c[:, 1, 2], c[:, 2, 2]], -1)
+    host = {"means3D": cat(lambda k: scs[k].means), "opacities": cat(lambda k: scs[k].opacities),
+            "shs": cat(lambda k: scs[k].harmonics.permute(0, 2, 1)), "cov3D_precomp": cat(lambda k: cov6(scs[k].covariances)),
+            "viewmatrix": cat(lambda k: vbs[k].viewmatrix), "projmatrix": cat(lambda k: vbs[k].projmatrix),
+            "campos": cat(lambda k: vbs[k].campos), "bg": cat(lambda k: scs[k].background), "tanfov": cat(lambda k: vbs[k].tanfov)}
+    cfg = _capi.GsConfig()
+    cfg.P, cfg.S, cfg.V, cfg.M, cfg.sh_degree = P, S, V, 25, 4
+    cfg.image_height, cfg.image_width, cfg.scale_modifier = hw[0], hw[1], 1.0
+    for k in ("viewmatrix", "projmatrix", "campos", "bg", "tanfov"):
+        setattr(cfg, k, host[k].data_ptr())
+    gin = _capi.GsInputs(means3D=host["means3D"].data_ptr(), opacities=host["opacities"].data_ptr(), shs=host["shs"].data_ptr(),
+                         cov3D_precomp=host["cov3D_precomp"].data_ptr())
+    color = torch.empty(V, 3, *hw).pin_memory()
+    radii = torch.empty(V, P, dtype=torch.int32).pin_memory()
+    gout = _capi.GsOutputs(color=color.data_ptr(), radii=radii.data_ptr(), depth=None)
+    ctx = rasterizer.current_context(dev)
+    ref = None
+    for tuning in (0, _capi.GS_TUNE_NO_SPLIT_COLOUR, _capi.GS_TUNE_NO_ZERO_COPY):
+        cfg.tuning = tuning | EXTRA
+        for rep in range(3):
+            _capi.check(_capi.lib().gs_render_host(ctx, ctypes.byref(cfg), ctypes.byref(gin), ctypes.byref(gout),
+                                                   torch.cuda.current_stream(dev).cuda_stream))
+            assert torch.isfinite(color).all()
+            ref = color.clone() if ref is None else ref
+            assert torch.equal(color, ref), (S, tuning)
+    print("ok host entry", S, P, V, hw)
+
 # ---- the rows next to the rasterizer: fused adapter (forward + backward), PSNR / SSIM ----
 from pf3plat_b200.adapter import GaussianAdapter, GaussianAdapterCfg  # noqa: E402
 from pf3plat_b200.metrics import compute_psnr, compute_ssim  # noqa: E402

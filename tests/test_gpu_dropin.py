@@ -232,6 +232,48 @@ def test_host_buffer_entry_matches_device_entry(P):
                                                torch.cuda.current_stream(dev).cuda_stream))
 
 
+def test_host_buffer_entry_with_two_scenes_and_pinned_inputs():
+    """gs_render_host, S = 2 scenes x 2 views each, pinned buffers: k_sh_colour's scene indexing (zero-copy feed) against the
+    device entry and against the copy-engine path."""
+    import ctypes
+    from pf3plat_b200 import _capi, rasterizer
+    from pf3plat_b200.cameras import make_view_batch
+    from pf3plat_b200.rasterizer import BatchSettings, rasterize_batch
+    dev = torch.device("cuda:0")
+    S, P, V, hw = 2, 9004, 4, (48, 64)     # P * 300 bytes is a multiple of 16: the second scene's block stays aligned
+    scs = [make_scene(P, V // S, *hw, seed=70 + k) for k in range(S)]
+    vbs = [make_view_batch(sc.extrinsics, sc.intrinsics, sc.near, sc.far) for sc in scs]
+    cat = lambda f: torch.cat([f(k) for k in range(S)]).contiguous().float().pin_memory()
+    cov6 = lambda c: torch.stack([c[:, 0, 0], c[:, 0, 1], c[:, 0, 2], c[:, 1, 1], c[:, 1, 2], c[:, 2, 2]], -1)
+    host = {"means3D": cat(lambda k: scs[k].means), "opacities": cat(lambda k: scs[k].opacities),
+            "shs": cat(lambda k: scs[k].harmonics.permute(0, 2, 1)), "cov3D_precomp": cat(lambda k: cov6(scs[k].covariances)),
+            "viewmatrix": cat(lambda k: vbs[k].viewmatrix), "projmatrix": cat(lambda k: vbs[k].projmatrix),
+            "campos": cat(lambda k: vbs[k].campos), "bg": cat(lambda k: scs[k].background), "tanfov": cat(lambda k: vbs[k].tanfov)}
+    d = {k: v.to(dev) for k, v in host.items()}
+    bs = BatchSettings(image_height=hw[0], image_width=hw[1], viewmatrix=d["viewmatrix"], projmatrix=d["projmatrix"],
+                       campos=d["campos"], bg=d["bg"], sh_degree=4, tanfov=d["tanfov"])
+    c2, r2 = rasterize_batch(bs, d["means3D"].reshape(S, P, 3), d["opacities"].reshape(S, P), shs=d["shs"].reshape(S, P, 25, 3),
+                             cov3D_precomp=d["cov3D_precomp"].reshape(S, P, 6))
+    cfg = _capi.GsConfig()
+    cfg.P, cfg.S, cfg.V, cfg.M, cfg.sh_degree = P, S, V, 25, 4
+    cfg.image_height, cfg.image_width, cfg.scale_modifier = hw[0], hw[1], 1.0
+    for k in ("viewmatrix", "projmatrix", "campos", "bg", "tanfov"):
+        setattr(cfg, k, host[k].data_ptr())
+    gin = _capi.GsInputs(means3D=host["means3D"].data_ptr(), opacities=host["opacities"].data_ptr(), shs=host["shs"].data_ptr(),
+                         cov3D_precomp=host["cov3D_precomp"].data_ptr())
+    color = torch.empty(V, 3, *hw).pin_memory()
+    radii = torch.empty(V, P, dtype=torch.int32).pin_memory()
+    gout = _capi.GsOutputs(color=color.data_ptr(), radii=radii.data_ptr(), depth=None)
+    ctx = rasterizer.current_context(dev)
+    for tuning in (0, _capi.GS_TUNE_NO_SPLIT_COLOUR, _capi.GS_TUNE_NO_ZERO_COPY):
+        cfg.tuning = tuning
+        for _ in range(3):
+            color.zero_(); radii.zero_()
+            _capi.check(_capi.lib().gs_render_host(ctx, ctypes.byref(cfg), ctypes.byref(gin), ctypes.byref(gout),
+                                                   torch.cuda.current_stream(dev).cuda_stream))
+            assert torch.equal(color, c2.cpu()) and torch.equal(radii, r2.cpu()), tuning
+
+
 def test_psnr_matches_the_reference_formula():
     """compute_psnr against the reference's formula (src/evaluation/metrics.py:11-19) evaluated in fp64."""
     from pf3plat_b200.metrics import compute_psnr
