@@ -13,4 +13,5 @@ dump gs_composite_fwd "15k_composite_fwdILb0" r2_k_composite_fwd_v1
 dump gs_composite_bwd "k_composite_bwdILb0ELi256" r2_k_composite_bwd_pair_matrix
 dump gs_composite_bwd "k_composite_bwd_v1ILb0" r2_k_composite_bwd_v1
 dump gs_binning "k_stratum_rank_sort" r2_k_stratum_rank_sort
+dump gs_preprocess "k_sh_colour" r2_k_sh_colour
 # (the per-kernel mnemonic histogram profiles/r2_sass_mnemonics.txt is written by a few lines of Python, see profiles/README.md)
