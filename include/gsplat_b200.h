@@ -192,6 +192,10 @@ GS_API int gs_get_stats(const GsContext *ctx, GsStats *out);
  * End-to-end entry with HOST buffers (what a non-torch plugin host calls): copies inputs to the device,
  * renders, copies color/radii[/depth] back, and synchronises.  All pointers in cfg/in/out are HOST pointers
  * here (pinned memory makes the copies asynchronous).  Forward only.
+ * An SH block (`in->shs`, M > 16) that sits in PINNED memory (cudaHostAlloc / cudaHostRegister, 16-byte aligned) is not
+ * copied: a kernel pulls the coefficients it evaluates straight out of the caller's buffer over PCIe while geometry,
+ * binning and the tile sort run.  The buffer must stay valid and unmodified until the call returns (it
+ * does: the call synchronises).  Pageable or unaligned blocks are uploaded by the copy engine; results are identical.
  */
 GS_API int gs_render_host(GsContext *ctx, const GsConfig *cfg, const GsInputs *in, const GsOutputs *out, void *stream);
 
