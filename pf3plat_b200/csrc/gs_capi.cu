@@ -790,9 +790,11 @@ extern "C" int gs_render_host(GsContext *ctx, const GsConfig *cfg, const GsInput
     };
     // ZERO-COPY FEED of the SH block (default when the caller's buffer is pinned and M > 16).  The block is most of the
     // bytes (C2: 150 of 170 MB) and the evaluator reads 192 of every 300-byte row.  Instead of the copy engine moving whole
-    // rows into a device buffer that preprocess then reads, preprocess pulls the 16-byte pieces it wants straight out of
-    // the host buffer while staging them into shared memory (k_preprocess, sh_raw16): no device copy of the block, no
-    // piece events, and the link carries 13 % fewer bytes (64-byte granularity: scripts/probes/pcie_pull_probe.cu).
+    // rows into a device buffer that a kernel then reads, the kernel that evaluates the colours pulls the 16-byte pieces it
+    // wants straight out of the host buffer while staging them into shared memory -- k_sh_colour on a second stream, with
+    // geometry, binning and the sort running meanwhile (gs_forward, split_colour), or the fused k_preprocess
+    // (GS_TUNE_NO_SPLIT_COLOUR): no device copy of the block, no piece events, and the link carries 13 % fewer bytes
+    // (64-byte granularity: scripts/probes/pcie_pull_probe.cu).
     void *sh_alias = nullptr;
     if (in->shs && cfg->M > 16 && !(cfg->tuning & GS_TUNE_NO_ZERO_COPY) &&
         (reinterpret_cast<uintptr_t>(in->shs) & 15u) == 0 && (cfg->S == 1 || ((size_t)cfg->P * cfg->M * 12) % 16 == 0))
@@ -884,7 +886,13 @@ extern "C" int gs_render_host(GsContext *ctx, const GsConfig *cfg, const GsInput
     ctx->sh_zero_copy = false;
     ctx->host_radii_dst = nullptr;
     ctx->feed_chunks = 0;
-    if (rc != GS_OK) return rc;
+    if (rc != GS_OK) {
+        // nothing of ours may still be reading the caller's buffers (the colour kernel pulls out of them) once we return
+        if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(st);
+        return rc;
+    }
     if (out->color && !color_alias) GS_CUDA_OK(cudaMemcpyAsync(out->color, dout.color, px * 12, cudaMemcpyDeviceToHost, st));
     if (out->depth && dout.depth && !depth_alias)
         GS_CUDA_OK(cudaMemcpyAsync(out->depth, dout.depth, px * 4, cudaMemcpyDeviceToHost, st));
