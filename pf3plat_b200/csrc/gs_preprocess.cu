@@ -370,16 +370,15 @@ k_preprocess(const DevCfg c, const DevInputs in, float4 *__restrict__ rec0, floa
 // of it.  gs_render_host therefore runs k_preprocess in geometry-only mode (COLOUR = 0) followed by the tile sort on the
 // launch stream, while THIS kernel, on a second stream, pulls the SH rows straight out of the caller's pinned buffer
 // (16-byte pieces at the rows' own stride, as k_preprocess's sh_raw16 mode) and writes rec1.zw / rec2.x; the compositor
-// waits for both.  Link-bound by design: a persistent grid of two CTAs per SM with a bounded number of host reads in
-// flight each (see launch_sh_colour) leaves the rest of every SM to the geometry kernel and the sort, which run underneath.
+// waits for both.  Link-bound by design: a persistent grid of three CTAs per SM keeps ~11 MB of host reads in flight (see
+// launch_sh_colour for what that does to the geometry kernel on the same SMs, and why it is still the fastest).
 // Same eval_sh / sh_view_dir as k_preprocess (pinned arithmetic): the split pipeline's images are bit-identical.
 constexpr int SHC_THREADS = 128;
 constexpr int SHC_VIEWS = 64;   // cameras staged at a time
 
-__global__ void __launch_bounds__(SHC_THREADS, 2)
+__global__ void __launch_bounds__(SHC_THREADS, 3)
 k_sh_colour(const DevCfg c, const float *__restrict__ means3D, const float *__restrict__ shs, float4 *__restrict__ rec1,
-            float4 *__restrict__ rec2, uint8_t *__restrict__ clamp_out /* [V*P] or NULL */, const int blocks_per_scene,
-            const int depth) {
+            float4 *__restrict__ rec2, uint8_t *__restrict__ clamp_out /* [V*P] or NULL */, const int blocks_per_scene) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4 *cam_s = reinterpret_cast<float4 *>(smem_raw);                    // (campos xyz, scale) per staged view
     float *sh_s = reinterpret_cast<float *>(smem_raw + SHC_VIEWS * sizeof(float4));
@@ -393,24 +392,12 @@ k_sh_colour(const DevCfg c, const float *__restrict__ means3D, const float *__re
         const size_t sg = (size_t)scene * c.P + g0 + tid;
         __syncthreads();   // the previous block's rows and cameras have been read by everybody
         {
-            // `depth` pieces per thread and group, two groups in flight: the reads this SM has outstanding over PCIe stay
-            // bounded (an SM whose miss queue is full of 2-microsecond host reads stalls every other warp's memory
-            // instructions -- the geometry kernel and the sort run on the same SMs)
             const float *src = shs + ((size_t)scene * c.P + g0) * row_f;
             const uint32_t nfl = (uint32_t)n * row_f, nq = nfl >> 2;
             const float4 *src4 = reinterpret_cast<const float4 *>(src);
-            int in_group = 0;
-            for (uint32_t q0 = 0; q0 < nq; q0 += SHC_THREADS) {   // (uniform trip count: the waits below are collective-free but cheap)
-                const uint32_t q = q0 + tid;
-                if (q < nq) {
-                    const uint32_t f0 = q << 2, r = f0 / row_f, c0 = f0 - r * row_f;
-                    if (c0 < want_f || c0 + 3u >= row_f) cp_async16(sh_s + f0, src4 + q);
-                }
-                if (++in_group == depth) {
-                    cp_async_commit();
-                    cp_async_wait<1>();
-                    in_group = 0;
-                }
+            for (uint32_t q = tid; q < nq; q += SHC_THREADS) {
+                const uint32_t f0 = q << 2, r = f0 / row_f, c0 = f0 - r * row_f;
+                if (c0 < want_f || c0 + 3u >= row_f) cp_async16(sh_s + f0, src4 + q);
             }
             for (uint32_t f = (nq << 2) + tid; f < nfl; f += SHC_THREADS)
                 if (f % row_f < want_f) cp_async4(sh_s + f, src + f);
@@ -506,18 +493,23 @@ int launch_sh_colour(const DevCfg &c, const DevInputs &in, float4 *rec1, float4 
     const int sms = (dev >= 0 && dev < 64 && sms_of_device[dev] > 0) ? sms_of_device[dev] : 148;
     const int bps = (c.P + SHC_THREADS - 1) / SHC_THREADS;
     const long long total = (long long)bps * c.S;
-    // Two CTAs per SM, two 16-byte pieces per thread and group (8 KB of host reads outstanding per CTA).  Measured on C2
-    // inside gs_render_host (scripts/probes/shc_sweep.sh; colour kernel / geometry / sort / whole call, ms):
-    //   3 CTAs, whole block at once  2.63 / 2.63 / 0.108 (after it) / 3.59-3.65   <- the other kernels starve until it ends
-    //   1 CTA,  2 pieces             2.71 / 0.50 / 0.33 / 3.60
-    //   2 CTAs, 2 pieces             2.84 / 1.02 / 0.67 / 3.61
-    //   1 CTA,  1 piece              2.87 / 0.33 / 0.20 / 3.84
-    // (alone, geometry takes 0.19 and the sort 0.107: the host reads in flight slow every memory instruction of the SM).
-    const int per_sm = 2, depth = 2;
+    // Three CTAs per SM, each issuing its block's pieces all at once: the link wants its reads deep.  What that does to the
+    // kernels sharing the SMs was the surprise -- an SM with host reads in flight slows all its other memory instructions in
+    // proportion (C2, inside gs_render_host; colour kernel / geometry / sort / whole call in ms; alone: geometry 0.19, sort
+    // 0.107; fused k_preprocess pulling the block instead: 3.64):
+    //   3 CTAs, whole block at once (this)   2.63 / 2.63 / 0.108 after it / 3.57-3.58   geometry ends WITH the pull, sort exposed
+    //   3 CTAs, 1 piece per thread and group 2.73 / 0.82 / 0.59 / 3.66                   (two groups in flight: cp.async.wait_group 1)
+    //   2 CTAs, 2 pieces                     2.84 / 1.02 / 0.67 / 3.61-3.62
+    //   1 CTA,  1 piece                      2.87 / 0.33 / 0.20 / 3.84
+    //   48 CTAs in all, whole block          2.76 / 0.33 / 0.25 / 3.65                   few SMs pulling: the interference is per SM
+    //   per-row bulk copies (TMA), 2 CTAs    2.68 / 2.04 / 0.63 / 3.53-3.66              same starvation: not the LSU queue
+    //   few reads until geometry + sort are done (a flag polled per block), then whole blocks: 2.80 / 0.82 / 0.60 / 3.64
+    // Hiding geometry + sort costs the pull more than the 0.3 ms they take; the pull at full rate wins.
+    const int per_sm = 3;
     const int grid = (int)(total < (long long)sms * per_sm ? total : (long long)sms * per_sm);
     const size_t smem = SHC_VIEWS * sizeof(float4) + (size_t)SHC_THREADS * c.M * 12;
     GS_CUDA_OK(cudaFuncSetAttribute(k_sh_colour, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_sh_colour<<<grid, SHC_THREADS, smem, st>>>(c, in.means3D, in.shs, rec1, rec2, clamp_out, bps, depth < 1 ? 1 : depth);
+    k_sh_colour<<<grid, SHC_THREADS, smem, st>>>(c, in.means3D, in.shs, rec1, rec2, clamp_out, bps);
     GS_CUDA_OK(cudaGetLastError());
     return GS_OK;
 }
