@@ -340,6 +340,7 @@ def main():
     ms_fwd = timed(fwd, args.steps, args.warmup, "fwd")
     launches_fwd = rasterizer.last_stats(dev)["kernel_launches"]   # of the last timed step (steady state)
     ms_e2e = timed(e2e, args.steps, args.warmup, "e2e")
+    launches_e2e = rasterizer.last_stats(dev)["kernel_launches"]   # 4 with the split pipeline (k_sh_colour), else 3
     ms_fb = timed(fwd_bwd, args.steps, args.warmup, "fwd_bwd")
     stats_fb = rasterizer.last_stats(dev)
 
@@ -445,7 +446,23 @@ def main():
             dist.all_gather(allr, mine)
         else:
             allr = [mine]
+        # forward + backward at this size too (MSE to a U(0,1) target, gradients to means / opacities / SH / covariances):
+        # north_star asks for fwd and fwd+bwd views/s at 512x512
+        leaves4 = {k: d4[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "cov3D_precomp")}
+        target4 = make_target(len(mine4), HW4, HW4, seed=5).to(dev)
+
+        def fwd_bwd4():
+            for t in leaves4.values():
+                t.grad = None
+            col4, _ = rasterize_batch(bs4, leaves4["means3D"], leaves4["opacities"], shs=leaves4["shs"],
+                                      cov3D_precomp=leaves4["cov3D_precomp"])
+            ((col4 - target4) ** 2).mean().backward()
+
+        ms4_fb = timed(fwd_bwd4, steps4, 3, "c4_fwd_bwd")
+        del leaves4, target4
         c4 = {"workload": WORKLOADS["c4"][3], "scaling": "strong", "views_total": V4, "views_per_gpu": len(mine4),
+              "fwd_bwd": {"ms_per_step": ms4_fb / steps4, "views_per_sec_512": V4 * steps4 / (ms4_fb * 1e-3),
+                          "gaussians_per_sec": P4 * V4 * steps4 / (ms4_fb * 1e-3), "loss": "MSE to U(0,1) target"},
               "steps": steps4, "ms_per_step": ms4 / steps4, "views_per_sec_512": V4 * steps4 / (ms4 * 1e-3),
               "gaussians_per_sec": P4 * V4 * steps4 / (ms4 * 1e-3), "tile_instances_rank0": st4["num_rendered"],
               "speculative": st4["speculative"], "first_loop_ms_per_step": ms4_first / steps4,
@@ -620,6 +637,7 @@ def main():
             "per_rank_ms_per_step": per_rank_ms or None,   # N > 1: every rank's own device time per step (value uses the max)
             "e2e": {"value": gauss_per_step * args.steps / (ms_e2e * 1e-3), "unit": "Gaussians/s",
                     "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "kernel_launches_per_call": launches_e2e,
                     "api": ("gs_render_host (C ABI, pinned host buffers; SH block pulled zero-copy by k_sh_colour: "
                             f"{sh_crossing} of its {sh_bytes} bytes requested in 16-byte pieces, the rest of the inputs copied)"
                             if zero_copy else "gs_render_host (C ABI, pinned host buffers, everything copied)") if world == 1 else
