@@ -151,6 +151,8 @@ typedef struct GsStats {
     int32_t max_tile_list;   /* longest (view, tile) list of the last forward */
     int32_t speculative;     /* last forward: 0 exact capacities; 1 speculative capacities (no count/scan/emit passes); 2 the same, binned by depth stratum */
     int32_t overflow_redos;  /* cumulative over the context's life: speculative forwards whose capacities overflowed and that were redone exactly */
+    int64_t pool_reserved_bytes; /* the context's private memory pool right now: physical memory it holds ... */
+    int64_t pool_used_bytes;     /* ... and how much of it is handed out (saved states alive + scratch) */
 } GsStats;
 
 typedef struct GsContext GsContext; /* per (device, caller) workspace; not thread-safe, one call at a time */

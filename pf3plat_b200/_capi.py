@@ -70,7 +70,8 @@ class GsInGrads(Structure):
 class GsStats(Structure):
     _fields_ = [("num_rendered", c_int64), ("num_visible", c_int64), ("saved_bytes", c_int64),
                 ("scratch_bytes", c_int64), ("kernel_launches", c_int32), ("max_tile_list", c_int32),
-                ("speculative", c_int32), ("overflow_redos", c_int32)]
+                ("speculative", c_int32), ("overflow_redos", c_int32), ("pool_reserved_bytes", c_int64),
+                ("pool_used_bytes", c_int64)]
 
 
 # every symbol include/gsplat_b200.h declares: name -> (restype, argtypes)

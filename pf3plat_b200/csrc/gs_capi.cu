@@ -64,6 +64,10 @@ struct GsContext {
     // gs_context_trim() / gs_context_destroy() hand everything back.
     cudaMemPool_t pool = nullptr;
     uint64_t pool_threshold = 0;
+    // forwards in a row that ran on the speculative path with the same saved-state size (pool_follow: the threshold is
+    // only tightened once a shape has settled)
+    int settled_calls = 0;
+    size_t settled_saved = 0;
     GrowBuf per_gaussian;  // rects | tile counts / offsets / cursors ; backward: accumulators
     GrowBuf sort;          // buckets (fast path) or radix-sort buffers (fallback)
     GrowBuf host_stage;    // device mirror of host buffers (gs_render_host)
@@ -292,14 +296,35 @@ extern "C" int gs_context_trim(GsContext *ctx) {
 
 namespace {
 // Keep about one forward's worth of freed saved state cached in the pool (the next forward takes it back), no more.
-void pool_follow(GsContext *ctx, size_t saved_bytes) {
+void pool_follow(GsContext *ctx, size_t saved_bytes, bool speculative_path) {
+    // While a shape is still settling -- exact call, strata trial, capacities re-learned, the backward's accumulator
+    // growing the scratch: block sizes change from call to call -- the pool keeps whatever it has: trimming it at every
+    // synchronisation made it hand blocks back and map them afresh (cuMemMap: ~0.2 ms per MB) for four to eight calls in a
+    // row (forward + backward at the C4 size: 0.4-1.8 s per step for the first five steps, 50-80 ms hiccups up to the eighth;
+    // scripts/probes/c4_fwd_bwd_probe.py).  Four calls in a row with the same saved-state size = settled: the threshold
+    // comes down to what a steady step needs and the pool trims once.
+    if (speculative_path && saved_bytes == ctx->settled_saved) ctx->settled_calls++;
+    else ctx->settled_calls = 0;
+    ctx->settled_saved = saved_bytes;
+    if (ctx->settled_calls < 4) {
+        if (ctx->pool_threshold != UINT64_MAX) {
+            ctx->pool_threshold = UINT64_MAX;
+            cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &ctx->pool_threshold);
+        }
+        return;
+    }
     // The threshold counts RESERVED bytes, in use or not: the grow-only scratch lives in the same pool and is always in
     // use, so it comes on top (without it the pool handed a forward's freed saved state back to the driver at every
     // synchronisation and mapped it afresh for the next call: 7 ms per forward at 16 views of C4, 2 GB each time).
     const uint64_t scratch = (ctx->per_gaussian.pooled ? ctx->per_gaussian.bytes : 0) + (ctx->sort.pooled ? ctx->sort.bytes : 0) +
                              (ctx->strata.pooled ? ctx->strata.bytes : 0);
-    const uint64_t want = scratch + (uint64_t)saved_bytes + (saved_bytes >> 2) + ((uint64_t)16 << 20);
-    if (want > ctx->pool_threshold || want < ctx->pool_threshold / 2) {
+    // TWO saved states: in the usual training loop (`out = render(...)` rebinding `out` every iteration) the previous
+    // iteration's graph -- and with it its saved state -- stays alive until the new forward has returned.  With room for
+    // one only, every step mapped a second saved state and the next synchronisation released it again (forward +
+    // backward at the C4 size: 33 instead of 21 ms per step).  The threshold is a cap on what the pool keeps, not a
+    // reservation: a loop that never holds two keeps one.
+    const uint64_t want = scratch + 2 * (uint64_t)saved_bytes + (saved_bytes >> 2) + ((uint64_t)16 << 20);
+    if (ctx->pool_threshold == UINT64_MAX || want > ctx->pool_threshold || want < ctx->pool_threshold / 2) {
         ctx->pool_threshold = want;
         cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &ctx->pool_threshold);
     }
@@ -334,6 +359,13 @@ extern "C" int gs_get_stats(const GsContext *ctx, GsStats *out) {
     if (!ctx || !out) return gs_set_error(GS_ERR_INVALID, "null argument");
     *out = ctx->stats;
     out->scratch_bytes = (int64_t)(ctx->per_gaussian.bytes + ctx->sort.bytes + ctx->host_stage.bytes);
+    uint64_t reserved = 0, used = 0;
+    if (ctx->pool) {
+        cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+        cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrUsedMemCurrent, &used);
+    }
+    out->pool_reserved_bytes = (int64_t)reserved;
+    out->pool_used_bytes = (int64_t)used;
     return GS_OK;
 }
 
@@ -594,7 +626,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
             ctx->stats.num_rendered = D;
             ctx->stats.num_visible = -1;
             ctx->stats.saved_bytes = (int64_t)(s->bytes + slots * sub_cap * 4);
-            pool_follow(ctx, (size_t)ctx->stats.saved_bytes);
+            pool_follow(ctx, (size_t)ctx->stats.saved_bytes, true);
             ctx->stats.speculative = strata ? 2 : 1;
             if (saved_out) *saved_out = s;
             else gs_saved_free(ctx, s, stream);
@@ -714,7 +746,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     ctx->stats.num_rendered = D;
     ctx->stats.num_visible = -1;
     ctx->stats.saved_bytes = (int64_t)(s->bytes + (size_t)(D > 0 ? D : 1) * 4);
-    pool_follow(ctx, (size_t)ctx->stats.saved_bytes);
+    pool_follow(ctx, (size_t)ctx->stats.saved_bytes, false);
     if (saved_out) {
         *saved_out = s;
     } else {
