@@ -323,7 +323,15 @@ void pool_follow(GsContext *ctx, size_t saved_bytes, bool speculative_path) {
     // one only, every step mapped a second saved state and the next synchronisation released it again (forward +
     // backward at the C4 size: 33 instead of 21 ms per step).  The threshold is a cap on what the pool keeps, not a
     // reservation: a loop that never holds two keeps one.
-    const uint64_t want = scratch + 2 * (uint64_t)saved_bytes + (saved_bytes >> 2) + ((uint64_t)16 << 20);
+    uint64_t want = scratch + 2 * (uint64_t)saved_bytes + (saved_bytes >> 2) + ((uint64_t)16 << 20);
+    if (ctx->pool_threshold == UINT64_MAX) {
+        // coming out of the settling phase: releasing is expensive in itself (C2: 58 ms at the next synchronisation + 34 ms
+        // in the following call for 32 MB), so what the pool holds is kept unless it is far more than a steady step needs
+        uint64_t reserved = 0;
+        cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+        const uint64_t roomy = want + want / 2;
+        if (reserved > want) want = reserved < roomy ? reserved : roomy;
+    }
     if (ctx->pool_threshold == UINT64_MAX || want > ctx->pool_threshold || want < ctx->pool_threshold / 2) {
         ctx->pool_threshold = want;
         cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &ctx->pool_threshold);

@@ -1,4 +1,6 @@
-"""Per-step wall time of forward+backward at the C4 size (2M Gaussians, 32 views, 512x512), with the library's counters."""
+"""Per-step wall time of forward+backward in the usual training-loop pattern (the previous step's output stays bound until
+the new forward has returned), default at the C4 size (2M Gaussians, 32 views, 512x512; GS_P / GS_V / GS_HW), with the
+library's counters."""
 import os, sys, time
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -7,7 +9,7 @@ from pf3plat_b200.cameras import make_view_batch
 from pf3plat_b200.rasterizer import BatchSettings, rasterize_batch
 from pf3plat_b200.synthetic import make_scene, make_target
 dev = torch.device("cuda:0")
-P, V, HW = 2_000_000, int(os.environ.get("GS_V", 32)), 512
+P, V, HW = int(os.environ.get("GS_P", 2_000_000)), int(os.environ.get("GS_V", 32)), int(os.environ.get("GS_HW", 512))
 sc = make_scene(P, V, HW, HW, seed=0)
 vb = make_view_batch(sc.extrinsics, sc.intrinsics, sc.near, sc.far, scale_invariant=True)
 c = sc.covariances
@@ -17,7 +19,7 @@ leaves = {k: v.contiguous().float().to(dev).requires_grad_(True) for k, v in d.i
 bs = BatchSettings(image_height=HW, image_width=HW, viewmatrix=vb.viewmatrix.to(dev), projmatrix=vb.projmatrix.to(dev), campos=vb.campos.to(dev),
                    bg=sc.background.to(dev), sh_degree=4, tanfov=vb.tanfov.to(dev))
 target = make_target(V, HW, HW, seed=5).to(dev)
-for it in range(14):
+for it in range(int(os.environ.get("GS_STEPS", 14))):
     if it == 4 and os.environ.get("GS_NOGRAD_BETWEEN"):
         with torch.no_grad():
             for _ in range(3):
