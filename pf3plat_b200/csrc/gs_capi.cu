@@ -58,16 +58,11 @@ struct GrowBuf {
 enum { STRATA_UNKNOWN = 0, STRATA_TRIAL = 1, STRATA_ON = 2, STRATA_OFF = 3 };
 
 struct GsContext {
-    // Private stream-ordered pool: saved state (records, lists, image planes) and scratch.  Blocks freed by
-    // gs_saved_free stay cached up to a release threshold that follows the size of ONE forward's saved state (so the
-    // next forward reuses them without touching the OS), never the device's default pool and never unbounded --
+    // Private stream-ordered pool: saved state (records, lists, image planes) and scratch -- never the device's default
+    // pool.  Blocks freed by gs_saved_free stay cached for the next calls (pool_follow: a periodic, bounded trim);
     // gs_context_trim() / gs_context_destroy() hand everything back.
     cudaMemPool_t pool = nullptr;
-    uint64_t pool_threshold = 0;
-    // forwards in a row that ran on the speculative path with the same saved-state size (pool_follow: the threshold is
-    // only tightened once a shape has settled)
-    int settled_calls = 0;
-    size_t settled_saved = 0;
+    int calls_since_peak_reset = 0;   // pool_follow: forwards since the pool's used-bytes high-water mark was last reset
     GrowBuf per_gaussian;  // rects | tile counts / offsets / cursors ; backward: accumulators
     GrowBuf sort;          // buckets (fast path) or radix-sort buffers (fallback)
     GrowBuf host_stage;    // device mirror of host buffers (gs_render_host)
@@ -252,6 +247,8 @@ extern "C" int gs_context_create(GsContext **out) {
         delete ctx;
         return gs_set_cuda_error(e, "cudaMemPoolCreate", __FILE__, __LINE__);
     }
+    uint64_t never = UINT64_MAX;   // freed blocks stay cached in the pool: see pool_follow
+    cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &never);
     e = cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_word), 64, cudaHostAllocMapped);
     if (e == cudaSuccess) e = cudaHostGetDevicePointer(reinterpret_cast<void **>(&ctx->d_word), ctx->h_word, 0);
     if (e != cudaSuccess) {
@@ -295,47 +292,28 @@ extern "C" int gs_context_trim(GsContext *ctx) {
 }
 
 namespace {
-// Keep about one forward's worth of freed saved state cached in the pool (the next forward takes it back), no more.
-void pool_follow(GsContext *ctx, size_t saved_bytes, bool speculative_path) {
-    // While a shape is still settling -- exact call, strata trial, capacities re-learned, the backward's accumulator
-    // growing the scratch: block sizes change from call to call -- the pool keeps whatever it has: trimming it at every
-    // synchronisation made it hand blocks back and map them afresh (cuMemMap: ~0.2 ms per MB) for four to eight calls in a
-    // row (forward + backward at the C4 size: 0.4-1.8 s per step for the first five steps, 50-80 ms hiccups up to the eighth;
-    // scripts/probes/c4_fwd_bwd_probe.py).  Four calls in a row with the same saved-state size = settled: the threshold
-    // comes down to what a steady step needs and the pool trims once.
-    if (speculative_path && saved_bytes == ctx->settled_saved) ctx->settled_calls++;
-    else ctx->settled_calls = 0;
-    ctx->settled_saved = saved_bytes;
-    if (ctx->settled_calls < 4) {
-        if (ctx->pool_threshold != UINT64_MAX) {
-            ctx->pool_threshold = UINT64_MAX;
-            cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &ctx->pool_threshold);
-        }
-        return;
-    }
-    // The threshold counts RESERVED bytes, in use or not: the grow-only scratch lives in the same pool and is always in
-    // use, so it comes on top (without it the pool handed a forward's freed saved state back to the driver at every
-    // synchronisation and mapped it afresh for the next call: 7 ms per forward at 16 views of C4, 2 GB each time).
-    const uint64_t scratch = (ctx->per_gaussian.pooled ? ctx->per_gaussian.bytes : 0) + (ctx->sort.pooled ? ctx->sort.bytes : 0) +
-                             (ctx->strata.pooled ? ctx->strata.bytes : 0);
-    // TWO saved states: in the usual training loop (`out = render(...)` rebinding `out` every iteration) the previous
-    // iteration's graph -- and with it its saved state -- stays alive until the new forward has returned.  With room for
-    // one only, every step mapped a second saved state and the next synchronisation released it again (forward +
-    // backward at the C4 size: 33 instead of 21 ms per step).  The threshold is a cap on what the pool keeps, not a
-    // reservation: a loop that never holds two keeps one.
-    uint64_t want = scratch + 2 * (uint64_t)saved_bytes + (saved_bytes >> 2) + ((uint64_t)16 << 20);
-    if (ctx->pool_threshold == UINT64_MAX) {
-        // coming out of the settling phase: releasing is expensive in itself (C2: 58 ms at the next synchronisation + 34 ms
-        // in the following call for 32 MB), so what the pool holds is kept unless it is far more than a steady step needs
-        uint64_t reserved = 0;
-        cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
-        const uint64_t roomy = want + want / 2;
-        if (reserved > want) want = reserved < roomy ? reserved : roomy;
-    }
-    if (ctx->pool_threshold == UINT64_MAX || want > ctx->pool_threshold || want < ctx->pool_threshold / 2) {
-        ctx->pool_threshold = want;
-        cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &ctx->pool_threshold);
-    }
+// Memory policy of the context's private pool.  Freed blocks stay in the pool (release threshold = never, set at creation):
+// every automatic scheme tried released memory that the very next calls mapped again, and both directions are expensive
+// (cuMemMap ~0.2 ms per MB; releasing 32 MB at a synchronisation: 58 ms, plus 34 ms in the following call):
+//   * threshold = scratch + 1.25 x saved state, updated every call: a shape that is still settling (exact call, strata
+//     trial, re-learned capacities, the backward's accumulator growing the scratch) changes its block sizes from call to call
+//     -- forward + backward at the C4 size took 0.4-1.8 s per step for five steps, with 50-80 ms hiccups up to the eighth;
+//   * the same once settled: the usual training loop (`out = render(...)`, rebinding `out`) keeps the previous step's saved
+//     state alive until the new forward has returned -- room for one meant mapping a second every step (33 instead of 21 ms);
+//   * room for two: the reference's decoder makes a call per view plus one per view for depth, and autograd holds all their
+//     saved states until the backward (12 at PF3plat's 2 x 3 views): 49 instead of 12.5 ms per step; following the pool's
+//     high-water mark fixed that but left hiccups whenever a capacity changed.
+// So, like the caching allocator of the host framework, the pool only gives memory back when asked (gs_context_trim /
+// rasterizer.trim_memory, gs_context_destroy) -- or here, every 256 calls, when it holds more than twice the high-water
+// mark of what those 256 calls had handed out at any one time (a one-off large batch does not pin its memory for ever).
+void pool_follow(GsContext *ctx) {
+    if (++ctx->calls_since_peak_reset < 256) return;
+    ctx->calls_since_peak_reset = 0;
+    uint64_t used_high = 0, reserved = 0, zero = 0;
+    cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrUsedMemHigh, &used_high);
+    cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+    if (reserved > 2 * used_high + ((uint64_t)64 << 20)) cudaMemPoolTrimTo(ctx->pool, used_high + (used_high >> 2));
+    cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrUsedMemHigh, &zero);
 }
 }  // namespace
 
@@ -634,7 +612,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
             ctx->stats.num_rendered = D;
             ctx->stats.num_visible = -1;
             ctx->stats.saved_bytes = (int64_t)(s->bytes + slots * sub_cap * 4);
-            pool_follow(ctx, (size_t)ctx->stats.saved_bytes, true);
+            pool_follow(ctx);
             ctx->stats.speculative = strata ? 2 : 1;
             if (saved_out) *saved_out = s;
             else gs_saved_free(ctx, s, stream);
@@ -754,7 +732,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     ctx->stats.num_rendered = D;
     ctx->stats.num_visible = -1;
     ctx->stats.saved_bytes = (int64_t)(s->bytes + (size_t)(D > 0 ? D : 1) * 4);
-    pool_follow(ctx, (size_t)ctx->stats.saved_bytes, false);
+    pool_follow(ctx);
     if (saved_out) {
         *saved_out = s;
     } else {
