@@ -57,6 +57,23 @@ struct GrowBuf {
 
 enum { STRATA_UNKNOWN = 0, STRATA_TRIAL = 1, STRATA_ON = 2, STRATA_OFF = 3 };
 
+// speculative bucket capacities learned from the previous forward of the same shape (0 = none yet)
+struct SpecState {
+    int V = 0, ntiles = 0;
+    uint32_t sub_cap = 0;     // capacity of one of a tile's BIN_SUB sub-buckets
+    uint32_t tile_limit = 0;  // list length the tile sort is launched for
+    // Depth strata (gs_binning.cu).  UNKNOWN: no boundaries for this shape yet.  TRIAL: boundaries learned by the
+    // last exact-path call, capacities still those of index % BIN_SUB sub-buckets -> the next speculative call
+    // tries strata with doubled capacities.  ON: strata with capacities learned from stratified counts.
+    // OFF: the trial overflowed (a tile whose depths crowd into one stratum): this shape stays on whole-tile sorts.
+    int strata_state = STRATA_UNKNOWN;
+    // Which boundaries `strata` holds: one row per view (octiles of the view's depths), or -- for shapes whose
+    // per-view trial overflowed: tiles that each see a narrow depth range, e.g. PF3plat's pixel-aligned Gaussians on
+    // a smooth surface -- one row per (view, tile), learned from the exact call's sorted lists and refreshed by the
+    // stratum sort of every call (two tables, swapped on success).
+    int strata_per_tile = 0, want_per_tile = 0, tile_tab = 0;
+};
+
 struct GsContext {
     // Private stream-ordered pool: saved state (records, lists, image planes) and scratch -- never the device's default
     // pool.  Blocks freed by gs_saved_free stay cached for the next calls (pool_follow: a periodic, bounded trim);
@@ -68,23 +85,20 @@ struct GsContext {
     GrowBuf host_stage;    // device mirror of host buffers (gs_render_host)
     uint32_t *d_word = nullptr;  // device alias of h_word (mapped pinned memory)
     uint32_t *h_word = nullptr;  // pinned, written by the device: [0] tile instances, [1] longest tile list, [2] largest sub-counter, [3] overflow
-    // speculative bucket capacities learned from the previous forward of the same shape (0 = none yet)
-    struct {
-        int V = 0, ntiles = 0;
-        uint32_t sub_cap = 0;     // capacity of one of a tile's BIN_SUB sub-buckets
-        uint32_t tile_limit = 0;  // list length the tile sort is launched for
-        // Depth strata (gs_binning.cu).  UNKNOWN: no boundaries for this shape yet.  TRIAL: boundaries learned by the
-        // last exact-path call, capacities still those of index % BIN_SUB sub-buckets -> the next speculative call
-        // tries strata with doubled capacities.  ON: strata with capacities learned from stratified counts.
-        // OFF: the trial overflowed (a tile whose depths crowd into one stratum): this shape stays on whole-tile sorts.
-        int strata_state = STRATA_UNKNOWN;
-        // Which boundaries `strata` holds: one row per view (octiles of the view's depths), or -- for shapes whose
-        // per-view trial overflowed: tiles that each see a narrow depth range, e.g. PF3plat's pixel-aligned Gaussians on
-        // a smooth surface -- one row per (view, tile), learned from the exact call's sorted lists and refreshed by the
-        // stratum sort of every call (two tables, swapped on success).
-        int strata_per_tile = 0, want_per_tile = 0, tile_tab = 0;
-    } spec;
-    GrowBuf strata;        // [V][BIN_SUB] stratum boundaries + histogram scratch
+    // What earlier forwards of a SHAPE (views, tiles, Gaussians per scene, scenes) taught: speculative bucket capacities,
+    // the strata state machine and its boundary tables.  A context remembers SHAPE_SLOTS shapes (least recently used one
+    // evicted), so a caller that alternates shapes -- context and target views of a training step, training and validation
+    // batches -- keeps every one of them on the speculative path; `spec` / `strata` point at the slot of the running call.
+    static constexpr int SHAPE_SLOTS = 4;
+    struct ShapeSlot {
+        int key_V = -1, key_ntiles = -1, key_P = -1, key_S = -1;
+        uint64_t last_use = 0;
+        SpecState spec;
+        GrowBuf strata;   // [V][BIN_SUB] (or two tables of [V*tiles][BIN_SUB]) stratum boundaries + histogram scratch
+    } slots[SHAPE_SLOTS];
+    uint64_t use_counter = 0;
+    SpecState *spec = &slots[0].spec;
+    GrowBuf *strata = &slots[0].strata;
     cudaEvent_t ev_pre = nullptr;   // "preprocess done" (speculative path: lets the radii copy start early)
     cudaEvent_t ev_info = nullptr;  // "binning verdict copied to the host"
     // gs_render_host's split pipeline: k_sh_colour pulls the SH block out of the caller's pinned buffer on aux_stream while
@@ -212,21 +226,21 @@ inline uint32_t sticky_capacity(uint32_t need, uint32_t current) {
 }
 
 void learn_capacities(GsContext *ctx, const DevCfg &c, uint32_t max_tile, uint32_t max_sub) {
-    const bool same_shape = ctx->spec.V == c.V && ctx->spec.ntiles == c.ntiles;
-    const uint32_t sub_cap = sticky_capacity(max_sub + max_sub * 3 / 10 + 16, same_shape ? ctx->spec.sub_cap : 0u);
-    const uint32_t limit = sticky_capacity(max_tile + max_tile / 10 + 32, same_shape ? ctx->spec.tile_limit : 0u);
+    const bool same_shape = ctx->spec->V == c.V && ctx->spec->ntiles == c.ntiles;
+    const uint32_t sub_cap = sticky_capacity(max_sub + max_sub * 3 / 10 + 16, same_shape ? ctx->spec->sub_cap : 0u);
+    const uint32_t limit = sticky_capacity(max_tile + max_tile / 10 + 32, same_shape ? ctx->spec->tile_limit : 0u);
     if (limit > BIN_SMEM_CAP || (uint64_t)sub_cap * BIN_SUB * c.V * c.ntiles > 0xffffffffull) {
-        ctx->spec.sub_cap = 0;  // lists too long for the shared-memory sort (or offsets beyond 32 bits): exact path
+        ctx->spec->sub_cap = 0;  // lists too long for the shared-memory sort (or offsets beyond 32 bits): exact path
         return;
     }
-    if (ctx->spec.V != c.V || ctx->spec.ntiles != c.ntiles) {
-        ctx->spec.strata_state = STRATA_UNKNOWN;
-        ctx->spec.strata_per_tile = ctx->spec.want_per_tile = 0;
+    if (ctx->spec->V != c.V || ctx->spec->ntiles != c.ntiles) {
+        ctx->spec->strata_state = STRATA_UNKNOWN;
+        ctx->spec->strata_per_tile = ctx->spec->want_per_tile = 0;
     }
-    ctx->spec.V = c.V;
-    ctx->spec.ntiles = c.ntiles;
-    ctx->spec.sub_cap = sub_cap;
-    ctx->spec.tile_limit = limit;
+    ctx->spec->V = c.V;
+    ctx->spec->ntiles = c.ntiles;
+    ctx->spec->sub_cap = sub_cap;
+    ctx->spec->tile_limit = limit;
 }
 
 }  // namespace
@@ -266,7 +280,7 @@ extern "C" void gs_context_destroy(GsContext *ctx) {
     ctx->per_gaussian.release();
     ctx->sort.release();
     ctx->host_stage.release();
-    ctx->strata.release();
+    for (auto &sl : ctx->slots) sl.strata.release();
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->ev_alloc) cudaEventDestroy(ctx->ev_alloc);
@@ -375,6 +389,21 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     const DevCfg c = make_dev_cfg(cfg);
     const DevInputs di = make_dev_inputs(in);
     const size_t n = (size_t)c.V * c.P;
+    {   // this shape's slot: what its earlier calls taught (GsContext::ShapeSlot); least recently used slot on a miss
+        GsContext::ShapeSlot *hit = nullptr, *lru = &ctx->slots[0];
+        for (auto &sl : ctx->slots) {
+            if (sl.key_V == c.V && sl.key_ntiles == c.ntiles && sl.key_P == c.P && sl.key_S == c.S) hit = &sl;
+            if (sl.last_use < lru->last_use) lru = &sl;
+        }
+        if (!hit) {
+            hit = lru;
+            hit->spec = SpecState{};   // (the slot's boundary buffer is kept and re-filled by the exact call)
+            hit->key_V = c.V; hit->key_ntiles = c.ntiles; hit->key_P = c.P; hit->key_S = c.S;
+        }
+        hit->last_use = ++ctx->use_counter;
+        ctx->spec = &hit->spec;
+        ctx->strata = &hit->strata;
+    }
     // gs_render_host with a pinned SH block: geometry-only preprocess here, colours by k_sh_colour on a second stream
     const bool split_colour = ctx->sh_zero_copy && !(cfg->tuning & GS_TUNE_NO_SPLIT_COLOUR) && n > 0 && sh_colour_supported(c, di);
     const int pre_low = ((cfg->tuning & GS_TUNE_PRE_OCC6) ? 1 : 0) | (((cfg->tuning & GS_TUNE_PRE_SH_RAW16) || ctx->sh_zero_copy) ? 2 : 0) |
@@ -460,13 +489,13 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
     // a one-CTA kernel right after preprocess checks that nothing overflowed, and the host reads its verdict only
     // after the tile sort and the compositor have been enqueued behind it.  On overflow the results are discarded
     // and the call is redone below on the exact path (which re-learns the capacities).
-    const bool speculate = ctx->spec.sub_cap > 0 && ctx->spec.V == c.V && ctx->spec.ntiles == c.ntiles && n > 0 &&
+    const bool speculate = ctx->spec->sub_cap > 0 && ctx->spec->V == c.V && ctx->spec->ntiles == c.ntiles && n > 0 &&
                            !(cfg->tuning & (GS_TUNE_FORCE_RADIX_BINNING | GS_TUNE_NO_SPECULATION));
     if (speculate) {
-        bool strata = (ctx->spec.strata_state == STRATA_TRIAL || ctx->spec.strata_state == STRATA_ON) &&
-                      !(cfg->tuning & GS_TUNE_NO_STRATA) && ctx->strata.p != nullptr;
-        uint32_t sub_cap = ctx->spec.sub_cap;
-        if (strata && ctx->spec.strata_state == STRATA_TRIAL) {
+        bool strata = (ctx->spec->strata_state == STRATA_TRIAL || ctx->spec->strata_state == STRATA_ON) &&
+                      !(cfg->tuning & GS_TUNE_NO_STRATA) && ctx->strata->p != nullptr;
+        uint32_t sub_cap = ctx->spec->sub_cap;
+        if (strata && ctx->spec->strata_state == STRATA_TRIAL) {
             // capacities were learned unstratified: the trial runs on doubled ones -- if the kernels' 32-bit bucket
             // offsets still hold them (learn_capacities checked the undoubled value only)
             // A cloud whose tiles each see a narrow depth range (PF3plat's pixel-aligned Gaussians on a smooth surface)
@@ -482,11 +511,11 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
             else sub_cap = trial;
         }
         if (strata && sub_cap > BIN_STRATUM_CAP) sub_cap = BIN_STRATUM_CAP;
-        const int per_tile = strata ? ctx->spec.strata_per_tile : 0;
+        const int per_tile = strata ? ctx->spec->strata_per_tile : 0;
         const size_t tab_floats = nvt * BIN_SUB;  // one per-tile table
-        float *tab0 = static_cast<float *>(ctx->strata.p);
-        const float *strata_tab = !strata ? nullptr : (per_tile ? tab0 + (size_t)ctx->spec.tile_tab * tab_floats : tab0);
-        float *strata_next = (strata && per_tile) ? tab0 + (size_t)(ctx->spec.tile_tab ^ 1) * tab_floats : nullptr;
+        float *tab0 = static_cast<float *>(ctx->strata->p);
+        const float *strata_tab = !strata ? nullptr : (per_tile ? tab0 + (size_t)ctx->spec->tile_tab * tab_floats : tab0);
+        float *strata_next = (strata && per_tile) ? tab0 + (size_t)(ctx->spec->tile_tab ^ 1) * tab_floats : nullptr;
         const size_t slots = nvt * BIN_SUB;
         rc = ctx->sort.reserve(slots * sub_cap * 8, 1.0, ctx->pool, st);
         if (rc != GS_OK) return fail(rc);
@@ -549,7 +578,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
         }
         if (!strata) {
             StageTimer t(ctx, GS_STAGE_BIN_SCAN, st);
-            rc = bin_spec_check(c, sub_cap, ctx->spec.tile_limit, cursor, ctx->d_word, st);
+            rc = bin_spec_check(c, sub_cap, ctx->spec->tile_limit, cursor, ctx->d_word, st);
             if (rc != GS_OK) return fail(rc);
             e = cudaEventRecord(ctx->ev_info, st);
             if (e != cudaSuccess) return fail(gs_set_cuda_error(e, "read back binning info", __FILE__, __LINE__));
@@ -564,7 +593,7 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
                 if (rc == GS_OK && (e = start_radii_copy()) != cudaSuccess)
                     return fail(gs_set_cuda_error(e, "early radii copy", __FILE__, __LINE__));
             } else {
-                rc = bin_sort_spec(c, sub_cap, ctx->spec.tile_limit, cursor, ctx->sort.p, s->point_list, s->ranges, st);
+                rc = bin_sort_spec(c, sub_cap, ctx->spec->tile_limit, cursor, ctx->sort.p, s->point_list, s->ranges, st);
             }
             if (rc != GS_OK) return fail(rc);
         }
@@ -582,22 +611,22 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
                 // capacities for the next call from the stratified counts just measured; a stratum beyond the small
                 // sort's capacity sends this shape back to whole-tile sorts (via one exact-path call)
                 uint32_t next = sticky_capacity(ctx->h_word[2] + ctx->h_word[2] * 3 / 10 + 16,
-                                                ctx->spec.strata_state == STRATA_ON ? sub_cap : 0u);
+                                                ctx->spec->strata_state == STRATA_ON ? sub_cap : 0u);
                 if (next > BIN_STRATUM_CAP && ctx->h_word[2] + ctx->h_word[2] / 10 <= BIN_STRATUM_CAP) next = BIN_STRATUM_CAP;  // 10 % headroom still fits
                 if (next > BIN_STRATUM_CAP) {
-                    ctx->spec.strata_state = STRATA_OFF;
-                    ctx->spec.sub_cap = 0;
+                    ctx->spec->strata_state = STRATA_OFF;
+                    ctx->spec->sub_cap = 0;
                 } else {
-                    if (ctx->spec.strata_state == STRATA_TRIAL && ctx->sort.bytes > 2 * (slots * (size_t)next * 8) + ((size_t)8 << 20)) {
+                    if (ctx->spec->strata_state == STRATA_TRIAL && ctx->sort.bytes > 2 * (slots * (size_t)next * 8) + ((size_t)8 << 20)) {
                         // the trial's generous buckets are not needed again: give the block back (stream-ordered)
                         if (ctx->sort.pooled) cudaFreeAsync(ctx->sort.p, st);
                         else cudaFree(ctx->sort.p);
                         ctx->sort.p = nullptr;
                         ctx->sort.bytes = 0;
                     }
-                    ctx->spec.strata_state = STRATA_ON;
-                    ctx->spec.sub_cap = next;
-                    if (per_tile) ctx->spec.tile_tab ^= 1;  // the sort wrote the next call's boundaries into the other table
+                    ctx->spec->strata_state = STRATA_ON;
+                    ctx->spec->sub_cap = next;
+                    if (per_tile) ctx->spec->tile_tab ^= 1;  // the sort wrote the next call's boundaries into the other table
                 }
             } else {
                 learn_capacities(ctx, c, ctx->h_word[1], ctx->h_word[2]);
@@ -620,14 +649,14 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
         }
         // overflow: some sub-bucket or tile list outgrew its capacity.  Results are invalid; redo exactly.
         ctx->stats.overflow_redos++;
-        ctx->spec.sub_cap = 0;
+        ctx->spec->sub_cap = 0;
         if (strata) {
-            if (ctx->spec.strata_state == STRATA_TRIAL && !per_tile && !(cfg->tuning & GS_TUNE_NO_TILE_STRATA)) {
+            if (ctx->spec->strata_state == STRATA_TRIAL && !per_tile && !(cfg->tuning & GS_TUNE_NO_TILE_STRATA)) {
                 // the per-view boundaries crowd some tile into one stratum: the exact redo below learns per-tile ones
-                ctx->spec.want_per_tile = 1;
-                ctx->spec.strata_state = STRATA_UNKNOWN;
+                ctx->spec->want_per_tile = 1;
+                ctx->spec->strata_state = STRATA_UNKNOWN;
             } else {
-                ctx->spec.strata_state = ctx->spec.strata_state == STRATA_TRIAL ? STRATA_OFF : STRATA_UNKNOWN;
+                ctx->spec->strata_state = ctx->spec->strata_state == STRATA_TRIAL ? STRATA_OFF : STRATA_UNKNOWN;
             }
         }
         if (ctx->host_radii_dst && ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
@@ -710,19 +739,19 @@ extern "C" int gs_forward(GsContext *ctx, const GsConfig *cfg, const GsInputs *i
 
     // Depth-stratum boundaries for the coming speculative calls, from this call's depths (off this call's critical
     // path: queued behind the compositor).  STRATA_OFF is sticky for the shape.
-    if (fast && ctx->spec.sub_cap > 0 && ctx->spec.strata_state != STRATA_OFF && !(cfg->tuning & GS_TUNE_NO_STRATA) && n > 0) {
-        rc = ctx->strata.reserve(bin_strata_bytes(c), 1.0, ctx->pool, st);
+    if (fast && ctx->spec->sub_cap > 0 && ctx->spec->strata_state != STRATA_OFF && !(cfg->tuning & GS_TUNE_NO_STRATA) && n > 0) {
+        rc = ctx->strata->reserve(bin_strata_bytes(c), 1.0, ctx->pool, st);
         if (rc != GS_OK) return fail(rc);
-        if (ctx->spec.want_per_tile) {
-            ctx->spec.tile_tab = 0;
-            rc = bin_learn_tile_strata(c, s->point_list, s->ranges, s->rec2, static_cast<float *>(ctx->strata.p), st);
+        if (ctx->spec->want_per_tile) {
+            ctx->spec->tile_tab = 0;
+            rc = bin_learn_tile_strata(c, s->point_list, s->ranges, s->rec2, static_cast<float *>(ctx->strata->p), st);
         } else {
-            rc = bin_learn_strata(c, rects, s->rec2, ctx->strata.p, st);
+            rc = bin_learn_strata(c, rects, s->rec2, ctx->strata->p, st);
         }
         if (rc != GS_OK) return fail(rc);
-        ctx->spec.strata_state = STRATA_TRIAL;
-        ctx->spec.strata_per_tile = ctx->spec.want_per_tile;
-        ctx->stats.kernel_launches += ctx->spec.want_per_tile ? 1 : 2;  // k_tile_octiles | k_depth_hist, k_strata_from_hist
+        ctx->spec->strata_state = STRATA_TRIAL;
+        ctx->spec->strata_per_tile = ctx->spec->want_per_tile;
+        ctx->stats.kernel_launches += ctx->spec->want_per_tile ? 1 : 2;  // k_tile_octiles | k_depth_hist, k_strata_from_hist
     }
 
     s->P = c.P; s->S = c.S; s->V = c.V; s->H = c.H; s->W = c.W;

@@ -293,6 +293,45 @@ def test_compositor_variants_agree():
                 assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max()) + 1e-12, tuning
 
 
+def test_alternating_shapes_keep_their_speculation_state():
+    """A context remembers several shapes: a caller that alternates two of them (context / target views of a training step,
+    training / validation batches) gets the speculative path for both from their third call on, with the pixels of the exact
+    path; cycling through more shapes than there are slots only evicts (every call exact or re-learning, still the same
+    pixels)."""
+    from pf3plat_b200._capi import GS_TUNE_NO_SPECULATION
+    from pf3plat_b200.cameras import make_view_batch
+    from pf3plat_b200.rasterizer import BatchSettings, last_stats, rasterize_batch
+    dev = _dev()
+
+    def shape(P, V, hw, seed):
+        sc = make_scene(P, V, *hw, seed=seed).to(dev)
+        vb = make_view_batch(sc.extrinsics, sc.intrinsics, sc.near, sc.far)
+        c = sc.covariances
+        cov6 = torch.stack([c[:, 0, 0], c[:, 0, 1], c[:, 0, 2], c[:, 1, 1], c[:, 1, 2], c[:, 2, 2]], -1)[None]
+        args = (sc.means[None], sc.opacities[None])
+        kw = dict(shs=sc.harmonics.permute(0, 2, 1).contiguous()[None], cov3D_precomp=cov6)
+        mk = lambda tuning: BatchSettings(image_height=hw[0], image_width=hw[1], viewmatrix=vb.viewmatrix, projmatrix=vb.projmatrix,
+                                          campos=vb.campos, bg=sc.background, sh_degree=4, tanfov=vb.tanfov, tuning=tuning)
+        with torch.no_grad():
+            ref = rasterize_batch(mk(GS_TUNE_NO_SPECULATION), *args, **kw)[0].clone()
+        return mk(0), args, kw, ref
+
+    shapes = [shape(20000, 2, (64, 80), 31), shape(30000, 3, (48, 48), 32)]
+    states = []
+    for it in range(5):
+        for bs, args, kw, ref in shapes:
+            with torch.no_grad():
+                out = rasterize_batch(bs, *args, **kw)[0]
+            assert torch.equal(out, ref)
+            states.append(last_stats(dev)["speculative"])
+    assert all(s >= 1 for s in states[4:]), states     # both shapes speculative from their third call on
+    more = shapes + [shape(10000 + 1000 * k, 1 + k % 3, (32, 48), 40 + k) for k in range(4)]
+    for it in range(3):
+        for bs, args, kw, ref in more:
+            with torch.no_grad():
+                assert torch.equal(rasterize_batch(bs, *args, **kw)[0], ref)
+
+
 def test_binning_paths_agree_bit_for_bit():
     """Exact-capacity buckets, speculative-capacity buckets (later calls of a shape; whole-tile sorts or depth strata)
     and the device-wide radix-sort fallback give the same lists, hence the same pixels; overflowing the learned
