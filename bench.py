@@ -458,11 +458,27 @@ def main():
                                       cov3D_precomp=leaves4["cov3D_precomp"])
             ((col4 - target4) ** 2).mean().backward()
 
-        ms4_fb = timed(fwd_bwd4, steps4, 3, "c4_fwd_bwd")
+        steps4_fb = max(8, args.steps // 2)
+        for _ in range(5):
+            fwd_bwd4()
+        barrier()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps4_fb + 1)]
+        evs[0].record(stream)
+        for k_ in range(steps4_fb):                      # one event per step: a hiccup shows as max >> median
+            fwd_bwd4()
+            evs[k_ + 1].record(stream)
+        barrier()
+        per_step4 = [evs[k_].elapsed_time(evs[k_ + 1]) for k_ in range(steps4_fb)]
+        ms4_fb_t = torch.tensor([evs[0].elapsed_time(evs[-1])], device=dev)
+        if world > 1:
+            dist.all_reduce(ms4_fb_t, op=dist.ReduceOp.MAX)
+        ms4_fb = float(ms4_fb_t.item())
         del leaves4, target4
         c4 = {"workload": WORKLOADS["c4"][3], "scaling": "strong", "views_total": V4, "views_per_gpu": len(mine4),
-              "fwd_bwd": {"ms_per_step": ms4_fb / steps4, "views_per_sec_512": V4 * steps4 / (ms4_fb * 1e-3),
-                          "gaussians_per_sec": P4 * V4 * steps4 / (ms4_fb * 1e-3), "loss": "MSE to U(0,1) target"},
+              "fwd_bwd": {"ms_per_step": ms4_fb / steps4_fb, "views_per_sec_512": V4 * steps4_fb / (ms4_fb * 1e-3),
+                          "gaussians_per_sec": P4 * V4 * steps4_fb / (ms4_fb * 1e-3), "loss": "MSE to U(0,1) target",
+                          "steps": steps4_fb, "median_step_ms_rank0": statistics.median(per_step4),
+                          "max_step_ms_rank0": max(per_step4)},
               "steps": steps4, "ms_per_step": ms4 / steps4, "views_per_sec_512": V4 * steps4 / (ms4 * 1e-3),
               "gaussians_per_sec": P4 * V4 * steps4 / (ms4 * 1e-3), "tile_instances_rank0": st4["num_rendered"],
               "speculative": st4["speculative"], "first_loop_ms_per_step": ms4_first / steps4,
