@@ -162,6 +162,37 @@ def test_batched_backward_sums_views_and_matches_oracle():
     check_grad("batched dL/dcov3D", g6, gc, aff)
 
 
+@pytest.mark.parametrize("blow_up", [25.0, 400.0])
+def test_huge_footprints_backward_matches_oracle(blow_up):
+    """A few Gaussians blown up to cover most of the image (every one reaches thousands of pixels in every tile): the
+    backward compositor's per-block moment sums are taken about the block centre and shifted to the Gaussian's own offset
+    (hundreds of pixels here) -- gradients against the oracle's direct per-pixel sums."""
+    dev = _dev()
+    views, P, hw = 2, 24, (48, 80)
+    sc = make_scene(P, views, *hw, seed=17)
+    sc.covariances.mul_(blow_up)
+    out, leaves = render_batch(sc, dev, requires_grad=True)
+    color = out[0] if isinstance(out, (tuple, list)) else out
+    target = make_target(views, *hw).to(dev)
+    ((color - target) ** 2).mean().backward()
+    gm = np.zeros((P, 3)); go = np.zeros(P); gs = np.zeros((P, 25, 3)); gc = np.zeros((P, 6))
+    aff = np.zeros(P, bool)
+    for v in range(views):
+        orc = oracle_view(sc, v)
+        aff |= affected_of(orc)
+        check_image(color[v], orc, max_fragile_frac=0.1)
+        dL = (2 * (orc.color - target[v].cpu().numpy()) / target.numel()).astype(np.float32)
+        g = orc.backward(dL)
+        gm += g["means3D"]; go += g["opacities"][:, 0]; gs += g["shs"]; gc += g["cov3D_precomp"]
+    aff[:] = False      # with two dozen Gaussians everything touches a fragile pixel: hold them all to the strict bound
+    check_grad(f"x{blow_up:g} dL/dmeans", leaves["means"].grad[0], gm, aff)
+    check_grad(f"x{blow_up:g} dL/dopacities", leaves["opac"].grad[0].reshape(-1, 1), go.reshape(-1, 1), aff)
+    check_grad(f"x{blow_up:g} dL/dshs", leaves["sh"].grad[0].permute(0, 2, 1), gs, aff, bands=SH_BANDS)
+    G = leaves["cov"].grad[0].cpu().numpy()
+    g6 = np.stack([G[:, 0, 0], G[:, 0, 1], G[:, 0, 2], G[:, 1, 1], G[:, 1, 2], G[:, 2, 2]], -1)
+    check_grad(f"x{blow_up:g} dL/dcov3D", g6, gc, aff)
+
+
 @pytest.mark.parametrize("d_sh,P", [(1, 1000), (4, 1001), (9, 777), (16, 1300), (16, 129), (25, 1301), (25, 63)])
 def test_sh_coefficient_counts_and_ragged_blocks(d_sh, P):
     """Every staging path of the SH block, forward and backward, against the oracle: M <= 16 (one bulk TMA copy when the
