@@ -88,5 +88,66 @@ for case in range(cases):
                 bad += 1
                 print("MISMATCH host entry", case, kind, P, V, hw, "pinned", pinned, "tuning", tuning)
     print(f"case {case:3d} {kind:10s} P={P:6d} V={V} hw={hw} depth={int(depth)} speculative per call {states}", flush=True)
+# ---- second part: two scenes per call, scales + rotations or covariances, SH or precomputed colours ----
+for case in range(cases // 2):
+    S = rng.choice([1, 2, 3])
+    vps = rng.randint(1, 3)
+    V = S * vps
+    hw = (rng.choice([24, 64, 96]), rng.choice([32, 64, 144]))
+    P = rng.choice([3, 500, 4000, 15000])
+    scs = [make_scene(P, vps, *hw, seed=5000 + 10 * case + k).to(dev) for k in range(S)]
+    vbs = [make_view_batch(sc.extrinsics, sc.intrinsics, sc.near, sc.far) for sc in scs]
+    cat = lambda f: torch.cat([f(k) for k in range(S)]).contiguous()
+    stack = lambda f: torch.stack([f(k) for k in range(S)]).contiguous()
+    use_sr, use_sh, depth = rng.random() < 0.5, rng.random() < 0.6, rng.random() < 0.5
+    kw = {}
+    if use_sh:
+        kw["shs"] = stack(lambda k: scs[k].harmonics.permute(0, 2, 1))
+    else:
+        kw["colors_precomp"] = cat(lambda k: scs[k].harmonics[:, :, 0][None].expand(vps, P, 3)).abs()
+    if use_sr:
+        kw["scales"] = stack(lambda k: scs[k].scales)
+        kw["rotations"] = stack(lambda k: scs[k].rotations)
+    else:
+        c6 = lambda c: torch.stack([c[:, 0, 0], c[:, 0, 1], c[:, 0, 2], c[:, 1, 1], c[:, 1, 2], c[:, 2, 2]], -1)
+        kw["cov3D_precomp"] = stack(lambda k: c6(scs[k].covariances))
+    means, opac = stack(lambda k: scs[k].means), stack(lambda k: scs[k].opacities)
+    mk = lambda tuning: BatchSettings(image_height=hw[0], image_width=hw[1], viewmatrix=cat(lambda k: vbs[k].viewmatrix),
+                                      projmatrix=cat(lambda k: vbs[k].projmatrix), campos=cat(lambda k: vbs[k].campos),
+                                      bg=cat(lambda k: scs[k].background), sh_degree=4, tanfov=cat(lambda k: vbs[k].tanfov),
+                                      view_scale=cat(lambda k: vbs[k].scale), with_depth=depth, tuning=tuning)
+    with torch.no_grad():
+        ref = [t.clone() for t in rasterize_batch(mk(_capi.GS_TUNE_NO_SPECULATION), means, opac, **kw)]
+        # every scene alone gives its own views of the batched call
+        for k in range(S):
+            one = BatchSettings(image_height=hw[0], image_width=hw[1], viewmatrix=vbs[k].viewmatrix, projmatrix=vbs[k].projmatrix,
+                                campos=vbs[k].campos, bg=scs[k].background, sh_degree=4, tanfov=vbs[k].tanfov, view_scale=vbs[k].scale,
+                                with_depth=depth, tuning=_capi.GS_TUNE_NO_SPECULATION)
+            kw1 = {n: (t[k * vps:(k + 1) * vps] if n == "colors_precomp" else t[k:k + 1]) for n, t in kw.items()}
+            alone = rasterize_batch(one, means[k:k + 1], opac[k:k + 1], **kw1)
+            for a, b in zip(alone, ref):
+                if not torch.equal(a, b[k * vps:(k + 1) * vps]):
+                    bad += 1
+                    print("MISMATCH scene alone vs batched", case, S, P, vps, hw, k)
+    for rep in range(4):
+        with torch.no_grad():
+            out = rasterize_batch(mk(0), means, opac, **kw)
+        for a, b in zip(out, ref):
+            if not torch.equal(a, b):
+                bad += 1
+                print("MISMATCH forward (scenes)", case, S, P, vps, hw, "rep", rep)
+    g = {}
+    for tuning in (0, _capi.GS_TUNE_BWD_V1 | _capi.GS_TUNE_PBWD_2PHASE):
+        lv = {n: t.clone().requires_grad_(True) for n, t in dict(kw, means=means, opac=opac).items()}
+        out = rasterize_batch(mk(tuning), lv["means"], lv["opac"], **{n: lv[n] for n in kw})
+        w = torch.randn(out[0].shape, generator=torch.Generator().manual_seed(case)).to(dev)
+        ((out[0] * w).sum() + (out[2].sum() * 0.01 if depth else 0.0)).backward()
+        g[tuning] = {n: t.grad for n, t in lv.items()}
+    for n in g[0]:
+        a, b = g[0][n], g[_capi.GS_TUNE_BWD_V1 | _capi.GS_TUNE_PBWD_2PHASE][n]
+        if float((a - b).abs().max()) > 2e-5 * float(b.abs().max()) + 1e-12 or not torch.isfinite(a).all():
+            bad += 1
+            print("MISMATCH backward (scenes)", case, n, S, P, vps, hw, float((a - b).abs().max()), float(b.abs().max()))
+    print(f"scenes case {case:3d} S={S} P={P:6d} views/scene={vps} hw={hw} sr={int(use_sr)} sh={int(use_sh)} depth={int(depth)}", flush=True)
 print("FUZZ", "FAILED" if bad else "ok", "mismatches", bad)
 sys.exit(1 if bad else 0)
