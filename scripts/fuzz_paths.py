@@ -51,6 +51,21 @@ for case in range(cases):
             if not torch.equal(a, b):
                 bad += 1
                 print("MISMATCH forward", case, kind, P, V, hw, "rep", rep, states, float((a.float() - b.float()).abs().max()))
+    # same shape, different content: the cloud pulled towards the optical axis (central tiles get several times the
+    # instances the capacities were learned for -> overflow, exact redo, re-learning), then the original again
+    if rng.random() < 0.5 and P > 100:
+        m2 = d.means.clone()
+        m2[:, :2] *= rng.choice([0.2, 0.5])
+        with torch.no_grad():
+            ref2 = [t.clone() for t in rasterize_batch(mk(_capi.GS_TUNE_NO_SPECULATION), m2[None], d.opacities[None], shs=shs, cov3D_precomp=cov6)]
+            redos0 = last_stats(dev)["overflow_redos"]
+            for means_k, ref_k in ((m2, ref2), (m2, ref2), (d.means, ref), (m2, ref2), (d.means, ref)):
+                out = rasterize_batch(mk(0), means_k[None], d.opacities[None], shs=shs, cov3D_precomp=cov6)
+                for a, b in zip(out, ref_k):
+                    if not torch.equal(a, b):
+                        bad += 1
+                        print("MISMATCH forward after content change", case, kind, P, V, hw)
+        overflow_seen = overflow_seen + (last_stats(dev)["overflow_redos"] - redos0) if "overflow_seen" in dir() else last_stats(dev)["overflow_redos"] - redos0
     # gradients: default kernels vs round-1 compositor + two-phase preprocess backward
     g = {}
     for tuning in (0, _capi.GS_TUNE_BWD_V1):
@@ -149,5 +164,5 @@ for case in range(cases // 2):
             bad += 1
             print("MISMATCH backward (scenes)", case, n, S, P, vps, hw, float((a - b).abs().max()), float(b.abs().max()))
     print(f"scenes case {case:3d} S={S} P={P:6d} views/scene={vps} hw={hw} sr={int(use_sr)} sh={int(use_sh)} depth={int(depth)}", flush=True)
-print("FUZZ", "FAILED" if bad else "ok", "mismatches", bad)
+print("FUZZ", "FAILED" if bad else "ok", "mismatches", bad, "| overflow redos provoked:", overflow_seen if "overflow_seen" in dir() else 0)
 sys.exit(1 if bad else 0)
