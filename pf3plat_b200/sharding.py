@@ -16,6 +16,14 @@ def shard_views(num_views: int, rank: int, world: int) -> range:
     return range(start, start + base + (1 if rank < extra else 0))
 
 
+def interleave_views(num_views: int, rank: int, world: int) -> range:
+    """Round-robin split: rank r takes views r, r + world, r + 2 world, ...  For views along a trajectory this gives every
+    rank the same mix of the trajectory (neighbouring views cost about the same), where contiguous blocks give each rank one
+    stretch of it: the ranks' workloads then differ by what their stretch happens to look at, and a synchronous job runs at
+    the pace of the heaviest stretch."""
+    return range(rank, num_views, world)
+
+
 def gather_metric(local: torch.Tensor) -> torch.Tensor:
     """All-gathers a 1-D per-view metric from every rank, concatenated in rank (= view) order.  Ragged shards are
     supported by padding to the longest shard."""

@@ -48,13 +48,14 @@ def quat_to_rotmat(q: torch.Tensor) -> torch.Tensor:
 
 
 def make_cameras(num_views: int, h: int, w: int, first_view: int = 0, total_views: int | None = None,
-                 phase: float = 0.0):
+                 phase: float = 0.0, view_stride: int = 1):
     """View 0 = identity; view k = translated on a circle of radius 0.1 in the image plane
-    (same construction as /root/reference/src/visualization/camera_trajectory/wobble.py:8-22)."""
+    (same construction as /root/reference/src/visualization/camera_trajectory/wobble.py:8-22).  The i-th camera returned
+    is view first_view + i * view_stride of the total_views on the circle."""
     total = total_views or num_views
     ext = torch.eye(4, dtype=torch.float32).repeat(num_views, 1, 1)
     for i in range(num_views):
-        k = first_view + i
+        k = first_view + i * view_stride
         if k > 0:
             ang = 2 * math.pi * k / total + phase
             ext[i, 0, 3] = 0.1 * math.cos(ang)
@@ -69,7 +70,7 @@ def make_cameras(num_views: int, h: int, w: int, first_view: int = 0, total_view
 
 
 def make_scene(num_gaussians: int, num_views: int, h: int, w: int, seed: int = 0, d_sh: int = 25,
-               first_view: int = 0, total_views: int | None = None) -> Scene:
+               first_view: int = 0, total_views: int | None = None, view_stride: int = 1) -> Scene:
     g = torch.Generator().manual_seed(seed)
     P = num_gaussians
 
@@ -95,7 +96,7 @@ def make_scene(num_gaussians: int, num_views: int, h: int, w: int, seed: int = 0
     if d_sh > 16:
         mask[16:] = 0.0
     sh = torch.randn(P, 3, d_sh, generator=g) * mask
-    ext, intr, near, far, bg = make_cameras(num_views, h, w, first_view, total_views)
+    ext, intr, near, far, bg = make_cameras(num_views, h, w, first_view, total_views, view_stride=view_stride)
     return Scene(ext, intr, near, far, (h, w), bg, means.contiguous(), cov.contiguous(), sh.contiguous(),
                  opac.contiguous(), scales.contiguous(), q.contiguous())
 

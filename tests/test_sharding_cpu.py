@@ -10,7 +10,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from pf3plat_b200.cameras import make_view_batch
-from pf3plat_b200.sharding import SharedCloudUploader, allreduce_scene_gradients, gather_metric, shard_views
+from pf3plat_b200.sharding import (SharedCloudUploader, allreduce_scene_gradients, gather_metric, interleave_views,
+                                   shard_views)
 from pf3plat_b200.synthetic import make_scene
 
 
@@ -61,6 +62,18 @@ def test_view_sharding_and_psnr_gather_world2():
     assert g0 == g1 == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0]    # every rank sees every view's metric, in view order
     full = make_scene(100, 8, 32, 32).extrinsics[:, :2, 3].tolist()
     assert t0 + t1 == full                                          # shards reproduce the unsharded camera path
+
+
+def test_interleaved_views_cover_everything_once_and_match_the_strided_cameras():
+    from pf3plat_b200.synthetic import make_cameras
+    for n, world in [(8, 1), (64, 8), (10, 4), (3, 5)]:
+        got = sorted(v for r in range(world) for v in interleave_views(n, r, world))
+        assert got == list(range(n))
+    full = make_cameras(64, 32, 32, total_views=64)[0]
+    for r in (0, 3, 7):
+        mine = interleave_views(64, r, 8)
+        ext = make_cameras(len(mine), 32, 32, first_view=mine[0], total_views=64, view_stride=8)[0]
+        assert torch.equal(ext, full[list(mine)])
 
 
 def test_shard_views_covers_ragged_splits():
