@@ -4,8 +4,11 @@
 // /root/reference/src/model/decoder/cuda_splatting.py:117-124).  B200 design:
 //  * one thread per Gaussian, LOOPING over the views of its scene, so the scene-level inputs (mean, covariance
 //    and the 300-byte SH block) are read from HBM once per call instead of once per view;
-//  * the CTA's contiguous SH block is staged into shared memory by ONE 1-D bulk TMA copy (cp.async.bulk,
-//    SASS UBLKCP) completing on an mbarrier -- fully coalesced, no register staging;
+//  * the coefficients the evaluator reads (bands 0..3: 16 of PF3plat's 25) are staged into shared memory -- one 1-D
+//    bulk TMA copy (cp.async.bulk, SASS UBLKCP) completing on an mbarrier when M <= 16, a 4-byte cp.async gather into
+//    odd-stride rows otherwise -- fully coalesced, no register staging;
+//  * k_sh_colour (below): the colour words alone, pulled out of PINNED HOST memory, for gs_render_host's split pipeline,
+//    with k_preprocess running geometry-only (COLOUR = 0) next to it;
 //  * outputs are three float4 SoA planes written with 16-byte stores;
 //  * tile binning keeps, of upstream's 3-sigma square, only the tiles the alpha >= 1/255 ellipse really reaches
 //    (exact box test), so tile lists only hold Gaussians that can contribute (identical pixels, -27 % instances).
